@@ -1,0 +1,531 @@
+"""CPU oracle for the GLIA reaction-diffusion forward/adjoint hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module restates, in NumPy/SciPy, the arithmetic
+of the reference's *CPU* path (PETSc KSPCG + AccFFT/FFTW conventions) in the
+reference's own operation order (3-D FFT gradient / divergence, 12 3-D FFTs per
+PCG iteration).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
+product (``glia_b200``) never does.
+
+Pinning: the reference cannot be compiled in this image
+(no MPI / PETSc / AccFFT / FFTW / PnetCDF), so the oracle is pinned against the
+reference's own known-answer tests instead:
+  K1  src/test/pdesolver.cpp:7-56    ||c||_2 == 2.0487, ksp_itr_ == 5
+  K2  src/test/simulator.cpp:94-95   ||c0||_2 == 4.09351   (atlas.nc)
+  K3  src/test/simulator.cpp:41-42   ||c0||_2 == 22.0161   (sinusoid.nc)
+(tests/test_oracle_pins.py).  A pure model-1 forward c(T), the adjoint alpha(t)
+and the kappa/rho gradient have no reference pin that runs without TAO:
+for those three quantities parity is "unpinned" and the oracle itself, anchored
+by K1-K3, is the reference.
+
+Third-party arithmetic restated here (not vendored under /root/reference):
+  * AccFFT accfft_grad / accfft_divergence / accfft_execute_r2c,c2r -- convention
+    taken from the only in-repo statement, src/cuda/SpectralOperators.cu:54-127
+    and src/grad/SpectralOperators.cpp:100-261.
+  * PETSc (3.7..3.11, doc/install.md:11) KSPCG with left preconditioning, the
+    preconditioned residual norm and KSPConvergedDefault with a non-zero initial
+    guess -- call sites src/pde/DiffusionSolver.cpp:19-44,241-243.
+
+All citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import scipy.fft as sfft
+
+_WORKERS = int(os.environ.get("GLIA_ORACLE_WORKERS", os.cpu_count() or 1))
+
+
+def set_workers(n: int) -> None:
+    global _WORKERS
+    _WORKERS = int(n)
+
+
+def get_workers() -> int:
+    return _WORKERS
+
+
+# --------------------------------------------------------------------------
+# L0  SpectralOperators
+# --------------------------------------------------------------------------
+def wavenumbers(n: int) -> np.ndarray:
+    """Signed integer wavenumbers with the Nyquist entry zeroed (trap T1).
+
+    src/cuda/SpectralOperators.cu:62-75, src/pde/DiffusionSolver.cpp:151-162.
+    """
+    w = np.arange(n, dtype=np.int64)
+    w[w > n // 2] -= n
+    w[n // 2] = 0
+    return w
+
+
+def fft_r2c(f: np.ndarray) -> np.ndarray:
+    """Unnormalised 3-D real-to-complex FFT, half spectrum along z.
+    src/grad/SpectralOperators.cpp:68-83."""
+    return sfft.rfftn(f, workers=_WORKERS)
+
+
+def fft_c2r(fhat: np.ndarray, shape) -> np.ndarray:
+    """Unnormalised inverse (forward . inverse = N . id).
+    src/grad/SpectralOperators.cpp:85-98."""
+    return sfft.irfftn(fhat, s=shape, norm="forward", workers=_WORKERS)
+
+
+def _mult_wave(fhat: np.ndarray, axis: int, shape) -> np.ndarray:
+    """w_f = (i * w_d / N) * f_hat, out of place.
+    src/cuda/SpectralOperators.cu:54-127 (factor = 1/(n0 n1 n2))."""
+    rdt = fhat.real.dtype
+    n = shape[axis]
+    factor = rdt.type(1.0 / (shape[0] * shape[1] * shape[2]))
+    w = wavenumbers(n)
+    if axis == 2:
+        w = w[: n // 2 + 1]
+    fw = (factor * w.astype(rdt)).astype(rdt)          # factor * wx, ScalarType
+    sh = [1, 1, 1]
+    sh[axis] = fw.shape[0]
+    fw = fw.reshape(sh)
+    out = np.empty_like(fhat)
+    out.real = -fw * fhat.imag
+    out.imag = fw * fhat.real
+    return out
+
+
+def gradient(f: np.ndarray, xyz=(1, 1, 1)):
+    """SpectralOperators::computeGradient -- 1 R2C + one multiply + C2R per
+    requested component.  src/grad/SpectralOperators.cpp:100-177."""
+    shape = f.shape
+    fhat = fft_r2c(f)
+    out = []
+    for d in range(3):
+        if xyz[d]:
+            out.append(fft_c2r(_mult_wave(fhat, d, shape), shape))
+        else:
+            out.append(None)
+    return out
+
+
+def divergence(dx: np.ndarray, dy: np.ndarray, dz: np.ndarray) -> np.ndarray:
+    """SpectralOperators::computeDivergence.  The real-space sum is taken in the
+    reference's order: x, then z, then y.  src/grad/SpectralOperators.cpp:179-261."""
+    shape = dx.shape
+    div = fft_c2r(_mult_wave(fft_r2c(dx), 0, shape), shape)
+    div = div + fft_c2r(_mult_wave(fft_r2c(dz), 2, shape), shape)
+    div = div + fft_c2r(_mult_wave(fft_r2c(dy), 1, shape), shape)
+    return div
+
+
+def weierstrass_smoother(c: np.ndarray, sigma: float) -> np.ndarray:
+    """SpectralOperators::weierstrassSmoother: periodic Gaussian built as a sum of
+    8 images, normalised by sum(f)*h^3, applied as F^-1[F(f) F(c)] h^3 / N.
+    src/grad/SpectralOperators.cpp:295-381 (no-op for sigma == 0, :272-274)."""
+    if sigma == 0:
+        return c.copy()
+    dt = c.dtype
+    n0, n1, n2 = c.shape
+    twopi = dt.type(2.0 * np.pi)
+    h = [dt.type(twopi / n) for n in (n0, n1, n2)]
+    s2 = dt.type(sigma)
+
+    def g1(n, hh):
+        X = (np.arange(n).astype(dt) * hh).astype(dt)
+        Xp = (X - twopi).astype(dt)
+        return X, Xp
+
+    X, Xp = g1(n0, h[0])
+    Y, Yp = g1(n1, h[1])
+    Z, Zp = g1(n2, h[2])
+
+    def e(a, b, cc):
+        A = (-a * a)[:, None, None]
+        B = (b * b)[None, :, None]
+        C = (cc * cc)[None, None, :]
+        with np.errstate(over="ignore", invalid="ignore"):
+            return np.exp(((A - B - C) / s2 / s2 / dt.type(2.0)).astype(dt)).astype(dt)
+
+    f = e(X, Y, Z) + e(Xp, Yp, Zp)
+    f = f + (e(Xp, Y, Z) + e(X, Yp, Z))
+    f = f + (e(X, Y, Zp) + e(Xp, Yp, Z))
+    f = f + (e(Xp, Y, Zp) + e(X, Yp, Zp))
+    f = f.astype(dt)
+    f[f != f] = 0
+    sum_f = dt.type(f.sum(dtype=np.float64))
+    norm = dt.type(1.0) / (sum_f * h[0] * h[1] * h[2])
+    f = (f * norm).astype(dt)
+    factor = dt.type(1.0 / (n0 * n1 * n2))
+    fh = fft_r2c(f)
+    ch = fft_r2c(c)
+    fh = fh * (ch * (factor * h[0] * h[1] * h[2]))
+    return fft_c2r(fh.astype(ch.dtype), c.shape).astype(dt)
+
+
+# --------------------------------------------------------------------------
+# L1  DiffCoef / ReacCoef
+# --------------------------------------------------------------------------
+class DiffCoef:
+    """Isotropic k(x) with kxx=kyy=kzz and kxy=kxz=kyz=0 (src/mat/DiffCoef.cpp:77-131)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.kxx = np.zeros(shape, dtype)
+        self.k_scale = self.dtype.type(1e-2)
+        self.kxx_avg = self.kyy_avg = self.kzz_avg = self.dtype.type(0)
+        self.kxy_avg = self.kxz_avg = self.kyz_avg = self.dtype.type(0)
+        self.ktilde = None          # temp_[7], setSecondaryCoefficients
+
+    def _avg(self, filter_sum):
+        t = self.dtype.type
+        s = t(self.kxx.sum(dtype=np.float64))
+        fa = t(filter_sum)
+        self.kxx_avg = self.kyy_avg = self.kzz_avg = t(s * (t(1.0) / fa))
+        self.kxy_avg = self.kxz_avg = self.kyz_avg = t(0)
+
+    def set_values(self, k_scale, k_gm_wm, k_glm_wm, wm, gm, csf, filt):
+        """DiffCoef::setValues (src/mat/DiffCoef.cpp:77-131): negative ratios clamp
+        to 0; averages normalised by the brain-mask voxel count (trap T5)."""
+        t = self.dtype.type
+        self.k_scale = t(k_scale)
+        dk_gm = t(k_scale) * t(k_gm_wm)
+        dk_wm = t(k_scale)
+        dk_glm = t(k_scale) * t(k_glm_wm)
+        dk_gm = t(0) if dk_gm <= 0 else dk_gm
+        dk_glm = t(0) if dk_glm <= 0 else dk_glm
+        k = np.zeros(self.shape, self.dtype)
+        k = k + dk_gm * gm
+        k = k + dk_wm * wm
+        k = k + dk_glm * csf
+        self.kxx = k.astype(self.dtype)
+        self._avg(filt.sum(dtype=np.float64))
+
+    def set_values_sinusoidal(self, scale):
+        """DiffCoef::setValuesSinusoidal (src/mat/DiffCoef.cpp:134-189)."""
+        t = self.dtype.type
+        n0, n1, n2 = self.shape
+        self.k_scale = t(scale)
+        freq = 4.0
+        X = np.sin(freq * 2.0 * np.pi / n0 * np.arange(n0))[:, None, None]
+        Y = np.sin(freq * 2.0 * np.pi / n1 * np.arange(n1))[None, :, None]
+        Z = np.sin(freq * 2.0 * np.pi / n2 * np.arange(n2))[None, None, :]
+        self.kxx = (float(t(scale)) * (0.5 + 0.5 * X * Y * Z)).astype(self.dtype)
+        self._avg(n0 * n1 * n2)
+
+    def set_secondary(self, k1, k2, k3, wm, gm, csf, nk=1, k_gm_wm=0.0, k_glm_wm=0.0):
+        """DiffCoef::setSecondaryCoefficients (src/mat/DiffCoef.cpp:44-59)."""
+        t = self.dtype.type
+        k1 = t(k1)
+        k2 = t(k_gm_wm) * k1 if nk == 1 else t(k2)
+        k3 = t(k_glm_wm) * k1 if nk == 1 else t(k3)
+        kt = (wm * k1).astype(self.dtype)
+        kt = kt + k2 * gm
+        kt = kt + k3 * csf
+        self.ktilde = kt.astype(self.dtype)
+
+    def apply_D(self, c, secondary=False):
+        """DiffCoef::applyD / applyDWithSecondaryCoeffs: grad -> K. -> div.
+        src/mat/DiffCoef.cpp:249-300 (off-diagonals identically 0, :94-100)."""
+        k = self.ktilde if secondary else self.kxx
+        gx, gy, gz = gradient(c)
+        return divergence(k * gx, k * gy, k * gz)
+
+
+def reac_coef(rho_scale, r_gm_wm, r_glm_wm, wm, gm, csf):
+    """ReacCoef::setValues (src/mat/ReacCoef.cpp:13-38)."""
+    t = wm.dtype.type
+    dr_gm = t(rho_scale) * t(r_gm_wm)
+    dr_wm = t(rho_scale)
+    dr_glm = t(rho_scale) * t(r_glm_wm)
+    dr_gm = t(0) if dr_gm <= 0 else dr_gm
+    dr_glm = t(0) if dr_glm <= 0 else dr_glm
+    rho = np.zeros_like(wm)
+    rho = rho + dr_gm * gm
+    rho = rho + dr_wm * wm
+    rho = rho + dr_glm * csf
+    return rho.astype(wm.dtype)
+
+
+# --------------------------------------------------------------------------
+# L2  DiffusionSolver  (Crank-Nicolson, PETSc-CG semantics)
+# --------------------------------------------------------------------------
+class DiffusionSolver:
+    """src/pde/DiffusionSolver.cpp:5-250.
+
+    ``dt_ctx`` is *state* (trap T2): initialised from params->tu_->dt_
+    (default 0.5, include/Parameters.h:166), overwritten by every solve();
+    precFactor() uses whatever value it holds at the time it is called.
+    """
+
+    RTOL = 1e-6
+    ABSTOL = 1e-50
+    DTOL = 1e4
+    MAXIT = 5000
+
+    def __init__(self, k: DiffCoef, dt_ctx=0.5):
+        self.k = k
+        self.dtype = k.dtype
+        self.dt_ctx = self.dtype.type(dt_ctx)
+        self.ksp_itr = 0
+        self.precfactor = None
+        self.prec_factor()
+
+    def prec_factor(self):
+        """DiffusionSolver::precFactor, CPU branch (:143-172).  The 0.25 / 2.0 / 1
+        literals promote the expression to double before it is stored as
+        ScalarType; the squares kxx_avg*wx*wx are ScalarType products."""
+        t = self.dtype.type
+        n0, n1, n2 = self.k.shape
+        factor = t(1.0 / (n0 * n1 * n2))
+        wx = wavenumbers(n0).astype(self.dtype)[:, None, None]
+        wy = wavenumbers(n1).astype(self.dtype)[None, :, None]
+        wz = wavenumbers(n2)[: n2 // 2 + 1].astype(self.dtype)[None, None, :]
+        k = self.k
+        txx = ((k.kxx_avg * wx).astype(self.dtype) * wx).astype(self.dtype).astype(np.float64)
+        tyy = ((k.kyy_avg * wy).astype(self.dtype) * wy).astype(self.dtype).astype(np.float64)
+        tzz = ((k.kzz_avg * wz).astype(self.dtype) * wz).astype(self.dtype).astype(np.float64)
+        txy = 2.0 * float(k.kxy_avg) * wx.astype(np.float64) * wy
+        txz = 2.0 * float(k.kxz_avg) * wx.astype(np.float64) * wz
+        tyz = 2.0 * float(k.kyz_avg) * wy.astype(np.float64) * wz
+        s = ((((txx + txy) + txz) + tyz) + tyy) + tzz
+        pf = (1 + 0.25 * float(self.dt_ctx) * s).astype(self.dtype)
+        out = np.empty_like(pf)
+        z = pf == 0
+        out[z] = factor
+        out[~z] = factor / pf[~z]
+        self.precfactor = out.astype(self.dtype)
+
+    def operator_A(self, x):
+        """y = x - (dt/2) D x  (:97-117); alph = -1/2*dt in ScalarType."""
+        alph = self.dtype.type(-1.0 / 2.0 * float(self.dt_ctx))
+        return (x + alph * self.k.apply_D(x)).astype(self.dtype)
+
+    def apply_pc(self, x):
+        """y = F^-1[ P_hat . F x ]  (:182-215)."""
+        xh = fft_r2c(x)
+        xh = xh * self.precfactor
+        return fft_c2r(xh, x.shape).astype(self.dtype)
+
+    @staticmethod
+    def _dot(a, b):
+        return float(np.dot(a.ravel().astype(np.float64), b.ravel().astype(np.float64)))
+
+    def solve(self, c, dt):
+        """DiffusionSolver::solve (:217-250) + KSPSolve_CG / KSPConvergedDefault
+        (PETSc 3.11 src/ksp/ksp/impls/cg/cg.c, src/ksp/ksp/interface/iterativ.c).
+        Returns the new c; sets ksp_itr."""
+        t = self.dtype.type
+        self.dt_ctx = t(dt)
+        if self.k.k_scale == 0:
+            self.ksp_itr = 0
+            return c
+        alph = t(1.0 / 2.0 * float(self.dt_ctx))
+        b = (c + alph * self.k.apply_D(c)).astype(self.dtype)
+
+        x = c.copy()
+        r = (b - self.operator_A(x)).astype(self.dtype)
+        z = self.apply_pc(r)
+        dp = np.sqrt(self._dot(z, z))
+        # KSPConvergedDefault at n == 0 with a non-zero initial guess
+        snorm = np.sqrt(self._dot(*(lambda zb: (zb, zb))(self.apply_pc(b))))
+        if snorm == 0:
+            snorm = dp
+        rnorm0 = snorm
+        ttol = max(self.RTOL * rnorm0, self.ABSTOL)
+        its = 0
+        if dp <= ttol:
+            self.ksp_itr = 0
+            return x
+        beta = 0.0
+        betaold = 1.0
+        p = None
+        while its < self.MAXIT:
+            if its == 0:
+                beta = self._dot(z, r)
+                if beta == 0.0:
+                    break
+                p = z.copy()
+            else:
+                bb = t(beta / betaold)
+                p = (z + bb * p).astype(self.dtype)
+            w = self.operator_A(p)
+            dpi = self._dot(p, w)
+            betaold = beta
+            a = t(beta / dpi)
+            x = (x + a * p).astype(self.dtype)
+            r = (r - a * w).astype(self.dtype)
+            z = self.apply_pc(r)
+            dp = np.sqrt(self._dot(z, z))
+            its += 1
+            if dp <= ttol:
+                break
+            if dp >= self.DTOL * rnorm0:
+                raise RuntimeError("KSP_DIVERGED_DTOL")
+            beta = self._dot(z, r)
+        self.ksp_itr = its
+        return x
+
+
+# --------------------------------------------------------------------------
+# L2a  PdeOperatorsRD
+# --------------------------------------------------------------------------
+def reaction_nonlinear(c, rho, dt):
+    """PdeOperatorsRD::reaction, linearized == 0 (src/pde/PdeOperators.cpp:161-169).
+    `1.0 - c` and `alph*factor + 1.0` are evaluated in double (trap T6)."""
+    t = c.dtype
+    factor = np.exp((rho * t.type(dt)).astype(t)).astype(t)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        alph = (c.astype(np.float64) / (1.0 - c.astype(np.float64))).astype(t)
+        af = (alph * factor).astype(t)
+        out = (af.astype(np.float64) / (af.astype(np.float64) + 1.0)).astype(t)
+    out[np.isinf(alph)] = 1.0
+    return out
+
+
+def reaction_linearized(u, c_lin, rho, dt):
+    """u <- u e^{rho dt} / (c e^{rho dt} + 1 - c)^2
+    (src/pde/PdeOperators.cpp:170-176 and :353-357)."""
+    t = u.dtype
+    factor = np.exp((rho * t.type(dt)).astype(t)).astype(t)
+    cf = (c_lin * factor).astype(t)
+    alph = ((cf.astype(np.float64) + 1.0) - c_lin.astype(np.float64)).astype(t)
+    uf = (u * factor).astype(t)
+    return (uf / (alph * alph).astype(t)).astype(t)
+
+
+class PdeOperatorsRD:
+    """Strang-split state / adjoint / incremental drivers with time histories.
+    src/pde/PdeOperators.cpp:140-420."""
+
+    def __init__(self, k: DiffCoef, rho: np.ndarray, nt: int, dt: float,
+                 dt_ctx=None, adjoint_store=True):
+        self.k = k
+        self.rho = rho
+        self.nt = int(nt)
+        self.dt = float(dt)
+        self.dtype = k.dtype
+        self.adjoint_store = adjoint_store
+        self.diff = DiffusionSolver(k, self.dt if dt_ctx is None else dt_ctx)
+        shape = k.shape
+        self.c_ = [np.zeros(shape, self.dtype) for _ in range(nt + 1)]
+        self.p_ = [np.zeros(shape, self.dtype) for _ in range(nt + 1)]
+        self.c_half_ = [np.zeros(shape, self.dtype) for _ in range(nt)]
+        self.ksp_state = 0
+        self.ksp_adj = 0
+        self.ksp_trace = []
+
+    def solve_incremental(self, c_tilde, i, mode, dt_half):
+        """src/pde/PdeOperators.cpp:192-233 (weights 1.5/0.5 exactly as coded)."""
+        t = self.dtype.type
+        tmp = (self.c_[i] + self.c_[i + 1]).astype(self.dtype)
+        tmp = (tmp * t(0.5)).astype(self.dtype)
+        tmp = (tmp + (self.c_[i] if mode == 1 else self.c_[i + 1])).astype(self.dtype)
+        tmp = self.k.apply_D(tmp, secondary=True).astype(self.dtype)
+        return (c_tilde + t(dt_half / 2) * tmp).astype(self.dtype)
+
+    def solve_state(self, c0, linearized=0):
+        """src/pde/PdeOperators.cpp:235-316."""
+        dt, nt = self.dt, self.nt
+        c = c0.astype(self.dtype).copy()
+        if linearized == 0:
+            self.c_[0] = c.copy()
+        self.ksp_state = 0
+        for i in range(nt):
+            if linearized == 2:
+                c = self.solve_incremental(c, i, 1, dt / 2)
+            c = self.diff.solve(c, dt / 2.0)
+            self.ksp_state += self.diff.ksp_itr
+            self.ksp_trace.append(self.diff.ksp_itr)
+            if linearized == 0 and self.adjoint_store:
+                self.c_half_[i] = c.copy()
+            if linearized == 0:
+                c = reaction_nonlinear(c, self.rho, dt)
+            else:
+                c = reaction_linearized(c, self.c_[i], self.rho, dt)
+            c = self.diff.solve(c, dt / 2.0)
+            self.ksp_state += self.diff.ksp_itr
+            self.ksp_trace.append(self.diff.ksp_itr)
+            if linearized == 2:
+                c = self.solve_incremental(c, i, 2, dt / 2)
+            if linearized == 0:
+                self.c_[i + 1] = c.copy()
+        return c
+
+    def solve_adjoint(self, pT, linearized=1):
+        """src/pde/PdeOperators.cpp:318-420.  p_[nt] is only written when
+        linearized == 1 (trap T4)."""
+        dt, nt = self.dt, self.nt
+        p = pT.astype(self.dtype).copy()
+        if linearized == 1:
+            self.p_[nt] = p.copy()
+        self.ksp_adj = 0
+        for i in range(nt):
+            p = self.diff.solve(p, dt / 2.0)
+            self.ksp_adj += self.diff.ksp_itr
+            self.ksp_trace.append(self.diff.ksp_itr)
+            it = nt - i - 1
+            if self.adjoint_store:
+                c_lin = self.c_half_[it]
+            else:
+                c_lin = self.diff.solve(self.c_[it].copy(), dt / 2.0)
+                self.ksp_adj += self.diff.ksp_itr
+            p = reaction_linearized(p, c_lin, self.rho, dt)
+            p = self.diff.solve(p, dt / 2.0)
+            self.ksp_adj += self.diff.ksp_itr
+            self.ksp_trace.append(self.diff.ksp_itr)
+            self.p_[it] = p.copy()
+        return p
+
+
+# --------------------------------------------------------------------------
+# L2b  gradient time integrals
+# --------------------------------------------------------------------------
+def grad_integrals(pde: PdeOperatorsRD):
+    """The two trapezoid time integrals of DerivativeOperators::gradDiffusion /
+    gradReaction (src/grad/DerivativeOperators.cpp:189-321), accumulated in
+    ScalarType exactly in the reference's order.  Returns (T_kappa, T_rho)."""
+    t = pde.dtype.type
+    nt = pde.nt
+    Tk = np.zeros(pde.k.shape, pde.dtype)
+    Tr = np.zeros(pde.k.shape, pde.dtype)
+    for i in range(nt + 1):
+        wgt = 0.5 if (i == 0 or i == nt) else 1.0
+        cx, cy, cz = gradient(pde.c_[i])
+        px, py, pz = gradient(pde.p_[i])
+        w0 = (cx * px).astype(pde.dtype)
+        w0 = (w0 + (cy * py).astype(pde.dtype)).astype(pde.dtype)
+        w0 = (w0 + (cz * pz).astype(pde.dtype)).astype(pde.dtype)
+        Tk = (Tk + t(pde.dt * wgt) * w0).astype(pde.dtype)
+        r0 = (pde.c_[i] * pde.c_[i]).astype(pde.dtype)
+        r0 = (r0 - pde.c_[i]).astype(pde.dtype)
+        r0 = (pde.p_[i] * r0).astype(pde.dtype)
+        Tr = (Tr + t(pde.dt * wgt) * r0).astype(pde.dtype)
+    return Tk, Tr
+
+
+def grad_kappa_rho(pde: PdeOperatorsRD, wm, gm, csf):
+    """Returns the six scalars h^3 <m, T_kappa>, h^3 <m, T_rho> for m = wm, gm, csf
+    (the caller combines them per nk / nr; src/grad/DerivativeOperators.cpp:231-249,
+    293-313)."""
+    n0, n1, n2 = pde.k.shape
+    leb = (2 * np.pi / n0) * (2 * np.pi / n1) * (2 * np.pi / n2)
+    Tk, Tr = grad_integrals(pde)
+    d = DiffusionSolver._dot
+    return np.array([leb * d(wm, Tk), leb * d(gm, Tk), leb * d(csf, Tk),
+                     leb * d(wm, Tr), leb * d(gm, Tr), leb * d(csf, Tr)])
+
+
+# --------------------------------------------------------------------------
+# fixtures shared by tests / bench
+# --------------------------------------------------------------------------
+def test_gaussian(n: int, dtype) -> np.ndarray:
+    """createTestFunction: exp(-r^2/R^2), R = sqrt(2) 2pi/64, centre (pi,pi,pi).
+    src/test/helper.cpp:19-49."""
+    dt = np.dtype(dtype)
+    R = dt.type(np.sqrt(2.0) * (2 * np.pi) / 64)
+    h = dt.type(2 * np.pi / n)
+    # dx = h*X - M_PI : ScalarType * int64 -> ScalarType, then minus a double
+    d = (h * np.arange(n).astype(dt)).astype(dt).astype(np.float64) - np.pi
+    d = d.astype(dt)
+    r = np.sqrt((d[:, None, None] ** 2 + d[None, :, None] ** 2 + d[None, None, :] ** 2).astype(dt)).astype(dt)
+    ratio = (r / R).astype(dt)
+    return np.exp(-(ratio * ratio)).astype(dt)
