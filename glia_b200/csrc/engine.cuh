@@ -1,0 +1,527 @@
+// engine.cuh -- host side of libglia_rd: buffers, sweep launch geometry, the PETSc-
+// semantics PCG loop, Strang time stepping with histories, gradient integrals.
+// Mirrors (does not copy) the control flow of the reference classes:
+//   DiffusionSolver   src/pde/DiffusionSolver.cpp:5-250
+//   PdeOperatorsRD    src/pde/PdeOperators.cpp:140-420
+//   DerivativeOperators::gradDiffusion/gradReaction  src/grad/DerivativeOperators.cpp:189-321
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pointwise.cuh"
+#include "sweeps.cuh"
+
+namespace glia {
+
+// ------------------------------------------------------------------ runtime ----
+namespace rt {
+#if defined(GLIA_SIMT_EMU)
+inline int dev_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 1; }
+inline void dev_free(void* p) { std::free(p); }
+inline int host_malloc(void** p, size_t n) { return dev_malloc(p, n); }
+inline void host_free(void* p) { std::free(p); }
+inline int copy(void* d, const void* s, size_t n, cudaStream_t) { std::memmove(d, s, n); return 0; }
+inline int h2d(void* d, const void* s, size_t n, cudaStream_t st) { return copy(d, s, n, st); }
+inline int d2h(void* d, const void* s, size_t n, cudaStream_t st) { return copy(d, s, n, st); }
+inline int zero(void* d, size_t n, cudaStream_t) { std::memset(d, 0, n); return 0; }
+inline int sync(cudaStream_t) { return 0; }
+inline int set_device(int) { return 0; }
+inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
+inline void stream_destroy(cudaStream_t) {}
+inline const char* err_string(int) { return "emu"; }
+struct Timer { void create() {} void destroy() {} void start(cudaStream_t) {} double stop_ms(cudaStream_t) { return 0; } };
+#else
+inline int dev_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline int host_malloc(void** p, size_t n) { return (int)cudaMallocHost(p, n ? n : 1); }
+inline void host_free(void* p) { if (p) cudaFreeHost(p); }
+inline int copy(void* d, const void* s, size_t n, cudaStream_t st) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st); }
+inline int h2d(void* d, const void* s, size_t n, cudaStream_t st) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st); }
+inline int d2h(void* d, const void* s, size_t n, cudaStream_t st) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st); }
+inline int zero(void* d, size_t n, cudaStream_t st) { return (int)cudaMemsetAsync(d, 0, n, st); }
+inline int sync(cudaStream_t st) { return (int)cudaStreamSynchronize(st); }
+inline int set_device(int d) { return (int)cudaSetDevice(d); }
+inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
+inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  void create() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+  void start(cudaStream_t st) { cudaEventRecord(a, st); }
+  double stop_ms(cudaStream_t st) {
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+#endif
+}  // namespace rt
+
+struct EngineError {
+  std::string msg;
+};
+
+#define GLIA_CHECK(expr)                                                                       \
+  do {                                                                                         \
+    int _e = (expr);                                                                           \
+    if (_e != 0) throw EngineError{std::string(#expr) + ": " + rt::err_string(_e)};            \
+  } while (0)
+
+#define GLIA_DISPATCH_N(nval, ...)                                         \
+  switch (nval) {                                                          \
+    case 32:  { constexpr int N = 32;  __VA_ARGS__; } break;               \
+    case 64:  { constexpr int N = 64;  __VA_ARGS__; } break;               \
+    case 128: { constexpr int N = 128; __VA_ARGS__; } break;               \
+    case 256: { constexpr int N = 256; __VA_ARGS__; } break;               \
+    case 512: { constexpr int N = 512; __VA_ARGS__; } break;               \
+    default: throw EngineError{"unsupported line length " + std::to_string(nval)}; \
+  }
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  std::string last_error;
+  long long launches = 0;
+  virtual int precision() const = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+ public:
+  using C = cplx<T>;
+  int n[3];
+  long nreal, ncplx;
+  int n2c;  // n2/2: complex columns of the pair view
+  cudaStream_t st = 0;
+  rt::Timer timer;
+
+  // coefficients
+  T *kf = nullptr, *ktil = nullptr, *rho = nullptr;
+  T kavg[3] = {0, 0, 0};
+  T k_scale = (T)1e-2;
+  T dt_ctx;
+  PcSym<T> sym;
+  // KSP settings (DiffusionSolver.cpp:27)
+  double rtol = 1e-6, abstol = 1e-50, dtol = 1e4;
+  int maxit = 5000;
+  // PCG work
+  T *b = nullptr, *r = nullptr, *z = nullptr, *p = nullptr, *w = nullptr, *acc = nullptr;
+  C* shat = nullptr;
+  C* tw[3] = {nullptr, nullptr, nullptr};
+  double *partial = nullptr, *scal = nullptr;
+  int* iscal = nullptr;
+  int* h_iscal = nullptr;     // pinned
+  double* h_out = nullptr;    // pinned
+  long npart = 0;             // doubles per partial region
+  int its_guess = 2;
+  // time stepping
+  int nt = 0;
+  T dt = 0;
+  T *c_hist = nullptr, *p_hist = nullptr, *chalf_hist = nullptr;
+  T *c_t = nullptr, *p_0 = nullptr, *work11 = nullptr, *Tk = nullptr, *Tr = nullptr;
+  // host staging for the host-buffer entry point
+  T *hs_in = nullptr, *hs_out = nullptr;
+
+  int precision() const override { return (int)sizeof(T); }
+
+  Engine(const int nn[3], int device, double dt_ctx_) {
+    for (int i = 0; i < 3; ++i) {
+      n[i] = nn[i];
+      if (!(n[i] == 32 || n[i] == 64 || n[i] == 128 || n[i] == 256 || n[i] == 512))
+        throw EngineError{"grid sizes must be powers of two in [32, 512]"};
+    }
+    GLIA_CHECK(rt::set_device(device));
+    GLIA_CHECK(rt::stream_create(&st));
+    timer.create();
+    nreal = (long)n[0] * n[1] * n[2];
+    ncplx = nreal / 2;
+    n2c = n[2] / 2;
+    dt_ctx = (T)dt_ctx_;
+    T** fields[] = {&kf, &ktil, &rho, &b, &r, &z, &p, &w, &acc, &c_t, &p_0, &work11, &Tk, &Tr};
+    for (T** f : fields) {
+      GLIA_CHECK(rt::dev_malloc((void**)f, sizeof(T) * nreal));
+      GLIA_CHECK(rt::zero(*f, sizeof(T) * nreal, st));
+    }
+    GLIA_CHECK(rt::dev_malloc((void**)&shat, sizeof(C) * ncplx));
+    for (int a = 0; a < 3; ++a) {
+      std::vector<C> tab(n[a]);
+      for (int j = 0; j < n[a]; ++j) {
+        const double ang = -2.0 * M_PI * (double)j / (double)n[a];
+        tab[j] = {(T)std::cos(ang), (T)std::sin(ang)};
+      }
+      GLIA_CHECK(rt::dev_malloc((void**)&tw[a], sizeof(C) * n[a]));
+      GLIA_CHECK(rt::h2d(tw[a], tab.data(), sizeof(C) * n[a], st));
+      GLIA_CHECK(rt::sync(st));
+    }
+    // partial-sum regions: enough for the largest grid of any reducing kernel
+    npart = 4 * (nreal / 256 + 1024);
+    GLIA_CHECK(rt::dev_malloc((void**)&partial, sizeof(double) * npart * 3));
+    GLIA_CHECK(rt::dev_malloc((void**)&scal, sizeof(double) * S_NSCAL));
+    GLIA_CHECK(rt::dev_malloc((void**)&iscal, sizeof(int) * I_NISCAL));
+    GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL, st));
+    GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL, st));
+    GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * I_NISCAL));
+    GLIA_CHECK(rt::host_malloc((void**)&h_out, sizeof(double) * 16));
+    sym = PcSym<T>{dt_ctx, (T)0, (T)0, (T)0, (T)(1.0 / ((double)n[0] * n[1] * n[2]))};
+    GLIA_CHECK(rt::sync(st));
+  }
+  ~Engine() override {
+    rt::sync(st);
+    T* fields[] = {kf, ktil, rho, b, r, z, p, w, acc, c_t, p_0, work11, Tk, Tr, c_hist, p_hist, chalf_hist};
+    for (T* f : fields) rt::dev_free(f);
+    rt::dev_free(shat);
+    for (int a = 0; a < 3; ++a) rt::dev_free(tw[a]);
+    rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal);
+    rt::host_free(h_iscal); rt::host_free(h_out);
+    rt::host_free(hs_in); rt::host_free(hs_out);
+    timer.destroy();
+    rt::stream_destroy(st);
+  }
+
+  void check_launch() {
+    const char* e = simt::last_error();
+    if (e) throw EngineError{std::string("kernel launch: ") + e};
+  }
+  void sync() { GLIA_CHECK(rt::sync(st)); check_launch(); }
+
+  // ------------------------------------------------------------ geometry ----
+  TileS tile_y() const { return TileS{(long)n2c, (long)n[1] * n2c, n2c / SL, n[0], 0}; }
+  TileS tile_x() const { return TileS{(long)n[1] * n2c, (long)n2c, n2c / SL, n[1], 0}; }
+  LinesZ lines_z() const { return LinesZ{(long)n[0] * n[1] / 2}; }
+  template <int N> static size_t smem_s() { return sizeof(C) * N * SL; }
+  template <int N> static size_t smem_z() { return sizeof(C) * zlines<N>() * zpad<N>(); }
+  template <int N> static dim3 block_s() { return dim3(SL * (N / FftPlan<N>::E)); }
+  static dim3 grid_s(const TileS& g) { return dim3(g.nchunk * g.n_outer); }
+  template <int N> dim3 grid_z() const {
+    const long np = lines_z().npairs;
+    return dim3((unsigned)((np + zlines<N>() - 1) / zlines<N>()));
+  }
+  static dim3 grid_pw(long nelem) {
+    long g = (nelem + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    return dim3((unsigned)g);
+  }
+  double* part(int region) { return partial + (long)region * npart; }
+
+  // ------------------------------------------------------------ sweeps ----
+  // acc = Dz(k Dz x); acc += Dy(k Dy x); then the x sweep with epilogue EPI
+  template <int EPI>
+  int dapply(const T* x, const T* kfield, T alpha, T* out1, T* out2, double* pp, const int* done) {
+    GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                       lines_z(), x, kfield, acc, (const C*)tw[2], done));
+    const TileS ty = tile_y(), tx = tile_x();
+    GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                       (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[1], (T)0, (C*)nullptr,
+                                       (C*)nullptr, (double*)nullptr, done));
+    GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                       (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[0], alpha, (C*)out1,
+                                       (C*)out2, pp, done));
+    launches += 3;
+    return (int)grid_s(tx).x;
+  }
+
+  // z = M^-1 r with optional prologue r -= a w, optional store, partial {<z,z>,<r,z>}
+  int pc_apply(T* rin, const T* wv, T* zout, bool want_rz, double* pp, const int* done) {
+    const TileS ty = tile_y(), tx = tile_x();
+    int nblk = 0;
+    if (wv) {
+      GLIA_DISPATCH_N(n[2], simt::launch(kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                         lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done));
+    } else {
+      GLIA_DISPATCH_N(n[2], simt::launch(kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                         lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
+                                         (const C*)tw[2], done));
+    }
+    GLIA_DISPATCH_N(n[1], simt::launch(ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                       (const C*)shat, shat, (const C*)tw[1], done));
+    GLIA_DISPATCH_N(n[0], simt::launch(ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
+                                       (const C*)tw[0], sym, n[1], done));
+    GLIA_DISPATCH_N(n[1], simt::launch(ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                       (const C*)shat, shat, (const C*)tw[1], done));
+    GLIA_DISPATCH_N(n[2], {
+      nblk = (int)grid_z<N>().x;
+      simt::launch(kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
+                   zout, want_rz ? (const T*)rin : (const T*)nullptr, pp, (const C*)tw[2], done);
+    });
+    launches += 5;
+    return nblk;
+  }
+
+  // ------------------------------------------------------------ L0 API ----
+  void gradient(T* gx, T* gy, T* gz, const T* x, int mask) {
+    const TileS ty = tile_y(), tx = tile_x();
+    if ((mask & 4) && gz) {
+      GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                         lines_z(), x, gz, (const C*)tw[2]));
+      launches++;
+    }
+    if ((mask & 2) && gy) {
+      GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv1<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                         (const C*)x, (C*)gy, (const C*)tw[1]));
+      launches++;
+    }
+    if ((mask & 1) && gx) {
+      GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv1<T, N, 0>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                         (const C*)x, (C*)gx, (const C*)tw[0]));
+      launches++;
+    }
+    sync();
+  }
+  void divergence(T* div, const T* dx, const T* dy, const T* dz) {
+    const TileS ty = tile_y(), tx = tile_x();
+    GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                       lines_z(), dz, div, (const C*)tw[2]));
+    GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv1<T, N, 1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                       (const C*)dy, (C*)div, (const C*)tw[1]));
+    GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv1<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                       (const C*)dx, (C*)div, (const C*)tw[0]));
+    launches += 3;
+    sync();
+  }
+
+  // ------------------------------------------------------------ L1 API ----
+  void set_diffusion(const T* k, const double ka[3], double kscale) {
+    GLIA_CHECK(rt::copy(kf, k, sizeof(T) * nreal, st));
+    for (int i = 0; i < 3; ++i) kavg[i] = (T)ka[i];
+    k_scale = (T)kscale;
+    sync();
+  }
+  void field_sum4(const T* t, const T* m0, const T* m1, const T* m2, double out[4]) {
+    const dim3 g = grid_pw(nreal);
+    simt::launch(k_dot3<T>, g, dim3(256), 0, st, nreal, t, m0, m1, m2, part(0));
+    simt::launch(k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8);
+    launches += 2;
+    GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
+    sync();
+    for (int i = 0; i < 4; ++i) out[i] = h_out[i];
+  }
+  void set_diffusion_tissue(const T* wm, const T* gm, const T* csf, double kscale, double kgm, double kglm,
+                            double filter_sum) {
+    // DiffCoef::setValues (src/mat/DiffCoef.cpp:77-131)
+    k_scale = (T)kscale;
+    T dk_gm = (T)kscale * (T)kgm, dk_wm = (T)kscale, dk_glm = (T)kscale * (T)kglm;
+    if (dk_gm <= 0) dk_gm = 0;
+    if (dk_glm <= 0) dk_glm = 0;
+    const dim3 g = grid_pw(nreal);
+    // kxx = 0; kxx += dk_gm*gm; kxx += dk_wm*wm; kxx += dk_glm*csf
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_gm, gm, (T)0, (const T*)nullptr);
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_wm, wm, (T)1, (const T*)kf);
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_glm, csf, (T)1, (const T*)kf);
+    launches += 3;
+    double s[4];
+    field_sum4(kf, nullptr, nullptr, nullptr, s);
+    const T ksum = (T)s[3];
+    const T favg = (T)filter_sum;
+    const T kav = ksum * ((T)1.0 / favg);
+    kavg[0] = kavg[1] = kavg[2] = kav;
+  }
+  void set_reaction_tissue(const T* wm, const T* gm, const T* csf, double rs, double rgm, double rglm) {
+    T dr_gm = (T)rs * (T)rgm, dr_wm = (T)rs, dr_glm = (T)rs * (T)rglm;
+    if (dr_gm <= 0) dr_gm = 0;
+    if (dr_glm <= 0) dr_glm = 0;
+    const dim3 g = grid_pw(nreal);
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_gm, gm, (T)0, (const T*)nullptr);
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_wm, wm, (T)1, (const T*)rho);
+    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_glm, csf, (T)1, (const T*)rho);
+    launches += 3;
+    sync();
+  }
+  void apply_D(T* dc, const T* c, bool secondary) {
+    const T* src = c;
+    if (dc == c) {  // the reference allows aliasing (PdeOperators.cpp:210)
+      GLIA_CHECK(rt::copy(work11, c, sizeof(T) * nreal, st));
+      src = work11;
+    }
+    dapply<EPI_PLAIN>(src, secondary ? ktil : kf, (T)0, dc, nullptr, nullptr, nullptr);
+    sync();
+  }
+
+  // ------------------------------------------------------------ L2 API ----
+  void prec_factor() {
+    sym.dt = dt_ctx;
+    sym.kxx = kavg[0];
+    sym.kyy = kavg[1];
+    sym.kzz = kavg[2];
+  }
+
+  void fetch_iscal() {
+    GLIA_CHECK(rt::d2h(h_iscal, iscal, sizeof(int) * I_NISCAL, st));
+    sync();
+  }
+
+  // one PCG iteration, enqueued without synchronisation; `it` is 1-based
+  void enqueue_iteration(T* x, T dt_solve, int it) {
+    const int* done = iscal + I_DONE;
+    const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
+    const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
+    simt::launch(k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal);
+    const int nb2 = pc_apply(r, w, z, true, part(1), done);
+    simt::launch(k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol);
+    simt::launch(k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
+                 (const int*)iscal, it);
+    launches += 3;
+  }
+
+  // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.
+  int diffusion_solve(T* x, double dt_in) {
+    const T dts = (T)dt_in;
+    dt_ctx = dts;  // side effect on later prec_factor() calls (trap T2)
+    if (k_scale == (T)0) return 0;
+    const T alph = (T)(1.0 / 2.0 * (double)dts);
+    dapply<EPI_RHS>(x, kf, alph, b, r, nullptr, nullptr);
+    const int nb0 = pc_apply(b, nullptr, nullptr, false, part(2), nullptr);
+    const int nb1 = pc_apply(r, nullptr, p, true, part(1), nullptr);
+    simt::launch(k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
+                 scal, iscal, rtol, abstol);
+    launches++;
+    int it = 0;
+    // speculate: enqueue as many iterations as the previous solve needed, then look
+    int burst = its_guess < 1 ? 1 : its_guess;
+    for (;;) {
+      for (int j = 0; j < burst; ++j) enqueue_iteration(x, dts, ++it);
+      fetch_iscal();
+      if (h_iscal[I_DONE]) break;
+      burst = 1;
+      if (it > maxit + 1) break;
+    }
+    const int its = h_iscal[I_ITS];
+    if (h_iscal[I_REASON] < 0 && h_iscal[I_REASON] != KSP_DIVERGED_ITS)
+      throw EngineError{"KSP diverged, reason " + std::to_string(h_iscal[I_REASON])};
+    its_guess = its;
+    return its;
+  }
+
+  // ------------------------------------------------------------ L2a API ----
+  void resize_history(int nt_, double dt_) {
+    sync();
+    rt::dev_free(c_hist); rt::dev_free(p_hist); rt::dev_free(chalf_hist);
+    c_hist = p_hist = chalf_hist = nullptr;
+    nt = nt_;
+    dt = (T)dt_;
+    GLIA_CHECK(rt::dev_malloc((void**)&c_hist, sizeof(T) * nreal * (nt + 1)));
+    GLIA_CHECK(rt::dev_malloc((void**)&p_hist, sizeof(T) * nreal * (nt + 1)));
+    GLIA_CHECK(rt::dev_malloc((void**)&chalf_hist, sizeof(T) * nreal * (nt > 0 ? nt : 1)));
+    GLIA_CHECK(rt::zero(c_hist, sizeof(T) * nreal * (nt + 1), st));
+    GLIA_CHECK(rt::zero(p_hist, sizeof(T) * nreal * (nt + 1), st));
+    GLIA_CHECK(rt::zero(chalf_hist, sizeof(T) * nreal * (nt > 0 ? nt : 1), st));
+    sync();
+  }
+  T* hist(int which, int i) {
+    if (which == 0 && i >= 0 && i <= nt) return c_hist + (long)i * nreal;
+    if (which == 1 && i >= 0 && i <= nt) return p_hist + (long)i * nreal;
+    if (which == 2 && i >= 0 && i < nt) return chalf_hist + (long)i * nreal;
+    throw EngineError{"history index out of range"};
+  }
+  void reaction(T* ct, const T* clin, T dtr, T* chalf_out) {
+    if (clin)
+      simt::launch(k_reaction_lin<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, clin, dtr);
+    else
+      simt::launch(k_reaction<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, dtr, chalf_out);
+    launches++;
+  }
+  // PdeOperatorsRD::solveIncremental
+  void solve_incremental(T* ctil, int i, int mode, T dth) {
+    simt::launch(k_incr_avg<T>, grid_pw(nreal), dim3(256), 0, st, nreal, work11, (const T*)hist(0, i),
+                 (const T*)hist(0, i + 1), mode == 1 ? 1 : 0);
+    launches++;
+    // c_tilde += dt/2 * D~ temp   (caller passes dt/2, the update uses dt/2 of that)
+    dapply<EPI_AXPY>(work11, ktil, (T)(dth / 2), ctil, nullptr, nullptr, nullptr);
+  }
+  int solve_state(const T* c0, T* cT, int linearized) {
+    if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
+    GLIA_CHECK(rt::copy(c_t, c0, sizeof(T) * nreal, st));
+    if (linearized == 0) GLIA_CHECK(rt::copy(hist(0, 0), c_t, sizeof(T) * nreal, st));
+    int total = 0;
+    const double dth = (double)dt / 2.0;
+    for (int i = 0; i < nt; ++i) {
+      if (linearized == 2) solve_incremental(c_t, i, 1, (T)dth);
+      total += diffusion_solve(c_t, dth);
+      if (linearized == 0) reaction(c_t, nullptr, dt, hist(2, i));
+      else reaction(c_t, hist(0, i), dt, nullptr);
+      total += diffusion_solve(c_t, dth);
+      if (linearized == 2) solve_incremental(c_t, i, 2, (T)dth);
+      if (linearized == 0) GLIA_CHECK(rt::copy(hist(0, i + 1), c_t, sizeof(T) * nreal, st));
+    }
+    if (cT) GLIA_CHECK(rt::copy(cT, c_t, sizeof(T) * nreal, st));
+    sync();
+    return total;
+  }
+  int solve_adjoint(const T* pT, T* p0out, int linearized, int adjoint_store) {
+    if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
+    GLIA_CHECK(rt::copy(p_0, pT, sizeof(T) * nreal, st));
+    if (linearized == 1) GLIA_CHECK(rt::copy(hist(1, nt), p_0, sizeof(T) * nreal, st));
+    int total = 0;
+    const double dth = (double)dt / 2.0;
+    for (int i = 0; i < nt; ++i) {
+      total += diffusion_solve(p_0, dth);
+      const int it = nt - i - 1;
+      const T* clin = hist(2, it);
+      if (!adjoint_store) {
+        GLIA_CHECK(rt::copy(work11, hist(0, it), sizeof(T) * nreal, st));
+        total += diffusion_solve(work11, dth);
+        clin = work11;
+      }
+      reaction(p_0, clin, dt, nullptr);
+      total += diffusion_solve(p_0, dth);
+      GLIA_CHECK(rt::copy(hist(1, it), p_0, sizeof(T) * nreal, st));
+    }
+    if (p0out) GLIA_CHECK(rt::copy(p0out, p_0, sizeof(T) * nreal, st));
+    sync();
+    return total;
+  }
+
+  // ------------------------------------------------------------ L2b API ----
+  void grad_kappa_rho(const T* wm, const T* gm, const T* csf, double out[6]) {
+    if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
+    GLIA_CHECK(rt::zero(Tk, sizeof(T) * nreal, st));
+    GLIA_CHECK(rt::zero(Tr, sizeof(T) * nreal, st));
+    const TileS ty = tile_y(), tx = tile_x();
+    for (int i = 0; i <= nt; ++i) {
+      const T wgt = (i == 0 || i == nt) ? (T)0.5 : (T)1.0;
+      const T coef = dt * wgt;
+      const T* ci = hist(0, i);
+      const T* pi = hist(1, i);
+      GLIA_DISPATCH_N(n[2], simt::launch(kz_gradprod<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                         lines_z(), ci, pi, Tk, Tr, coef, (const C*)tw[2]));
+      GLIA_DISPATCH_N(n[1], simt::launch(ks_gradprod<T, N>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+                                         (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[1]));
+      GLIA_DISPATCH_N(n[0], simt::launch(ks_gradprod<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                         (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[0]));
+      launches += 3;
+    }
+    const double leb = (2.0 * M_PI / n[0]) * (2.0 * M_PI / n[1]) * (2.0 * M_PI / n[2]);
+    double s[4];
+    field_sum4(Tk, wm, gm, csf, s);
+    out[0] = leb * s[0]; out[1] = leb * s[1]; out[2] = leb * s[2];
+    field_sum4(Tr, wm, gm, csf, s);
+    out[3] = leb * s[0]; out[4] = leb * s[1]; out[5] = leb * s[2];
+  }
+
+  // ------------------------------------------------- host-buffer entry ----
+  void forward_adjoint_host(const T* c0h, const T* d1h, T* cTh, T* p0h, int* ks, int* ka) {
+    // pinned staging so the copies are true async DMA; device scratch: b (c0), w (d1)
+    if (!hs_in) {
+      GLIA_CHECK(rt::host_malloc((void**)&hs_in, sizeof(T) * nreal * 2));
+      GLIA_CHECK(rt::host_malloc((void**)&hs_out, sizeof(T) * nreal * 2));
+    }
+    std::memcpy(hs_in, c0h, sizeof(T) * nreal);
+    std::memcpy(hs_in + nreal, d1h, sizeof(T) * nreal);
+    GLIA_CHECK(rt::h2d(Tk, hs_in, sizeof(T) * nreal, st));
+    GLIA_CHECK(rt::h2d(Tr, hs_in + nreal, sizeof(T) * nreal, st));
+    *ks = solve_state(Tk, Tk, 0);
+    // p_T = -(c(T) - d1)
+    simt::launch(k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, Tr, (T)1, (const T*)Tr, (T)-1, (const T*)Tk);
+    launches++;
+    *ka = solve_adjoint(Tr, Tr, 1, 1);
+    GLIA_CHECK(rt::d2h(hs_out, Tk, sizeof(T) * nreal, st));
+    GLIA_CHECK(rt::d2h(hs_out + nreal, Tr, sizeof(T) * nreal, st));
+    sync();
+    std::memcpy(cTh, hs_out, sizeof(T) * nreal);
+    std::memcpy(p0h, hs_out + nreal, sizeof(T) * nreal);
+  }
+};
+
+}  // namespace glia

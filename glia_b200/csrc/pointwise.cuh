@@ -1,0 +1,213 @@
+// pointwise.cuh -- streaming kernels of the RD path: logistic reaction, PCG vector
+// updates, device-resident PCG scalars, reductions.
+#pragma once
+#include "fft_core.cuh"
+
+namespace glia {
+
+__device__ __forceinline__ float g_exp(float x) { return expf(x); }
+__device__ __forceinline__ double g_exp(double x) { return exp(x); }
+template <typename T>
+__device__ __forceinline__ bool g_isinf(T x) { return x == x && (x - x) != (x - x); }
+
+// ---- device-resident PCG state (one block per solver handle) --------------
+enum { S_BETA = 0, S_BETAOLD, S_A, S_B, S_DP, S_RNORM0, S_TTOL, S_DPI, S_NSCAL = 16 };
+enum { I_ITS = 0, I_DONE, I_TOTAL, I_REASON, I_NISCAL = 8 };
+// reasons follow PETSc's KSPConvergedReason values
+enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_DIVERGED_ITS = -3, KSP_DIVERGED_DTOL = -4,
+       KSP_DIVERGED_NANORINF = -9, KSP_DIVERGED_INDEFINITE_MAT = -10 };
+
+template <int NV>
+__device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int n, double (&out)[NV]) {
+  // fixed-order (deterministic) two-level sum by one CTA of 256 threads
+  __shared__ double sh[256 * NV];
+  const int tid = threadIdx.x;
+  double acc[NV];
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (int j = tid; j < n; j += 256)
+    GLIA_UNROLL
+    for (int i = 0; i < NV; ++i) acc[i] += partial[(size_t)j * NV + i];
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) sh[tid * NV + i] = acc[i];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s)
+      GLIA_UNROLL
+      for (int i = 0; i < NV; ++i) sh[tid * NV + i] += sh[(tid + s) * NV + i];
+    __syncthreads();
+  }
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) out[i] = sh[i];
+  __syncthreads();
+}
+
+// KSPConvergedDefault at iteration 0 with a non-zero initial guess:
+//   rnorm0 = ||M^-1 b|| (or dp if that is 0), ttol = max(rtol*rnorm0, abstol), test dp <= ttol.
+__global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
+                           double rtol, double abstol) {
+  double b[2], rz[2];
+  sum_partials<2>(pb, nb, b);
+  sum_partials<2>(prz, nrz, rz);
+  if (threadIdx.x == 0) {
+    const double dp = sqrt(rz[0]);
+    double rnorm0 = sqrt(b[0]);
+    if (rnorm0 == 0.0) rnorm0 = dp;
+    const double ttol = fmax(rtol * rnorm0, abstol);
+    scal[S_DP] = dp; scal[S_RNORM0] = rnorm0; scal[S_TTOL] = ttol;
+    scal[S_BETA] = rz[1]; scal[S_BETAOLD] = 1.0; scal[S_A] = 0.0; scal[S_B] = 0.0;
+    iscal[I_ITS] = 0;
+    int done = 0, reason = 0;
+    if (dp != dp) { done = 1; reason = KSP_DIVERGED_NANORINF; }
+    else if (dp <= ttol) { done = 1; reason = dp < abstol ? KSP_CONVERGED_ATOL : KSP_CONVERGED_RTOL; }
+    else if (rz[1] == 0.0) { done = 1; reason = KSP_CONVERGED_ATOL; }
+    iscal[I_DONE] = done; iscal[I_REASON] = reason;
+  }
+}
+
+// a = beta / <p, A p>
+template <typename T>
+__global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal) {
+  if (iscal[I_DONE]) return;
+  double d[1];
+  sum_partials<1>(ppw, n, d);
+  if (threadIdx.x == 0) {
+    scal[S_DPI] = d[0];
+    scal[S_BETAOLD] = scal[S_BETA];
+    scal[S_A] = (double)(T)(scal[S_BETA] / d[0]);
+    if (!(d[0] > 0.0)) { iscal[I_REASON] = KSP_DIVERGED_INDEFINITE_MAT; iscal[I_TOTAL] += iscal[I_ITS]; iscal[I_DONE] = 1; }
+  }
+}
+
+// after z = M^-1 r: dp = ||z||, its++, convergence test, beta = <r,z>, b = beta/betaold
+template <typename T>
+__global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, int maxit, double dtol) {
+  if (iscal[I_DONE]) return;
+  double rz[2];
+  sum_partials<2>(prz, n, rz);
+  if (threadIdx.x == 0) {
+    const double dp = sqrt(rz[0]);
+    scal[S_DP] = dp;
+    const int its = iscal[I_ITS] + 1;
+    iscal[I_ITS] = its;
+    int done = 0, reason = 0;
+    if (dp != dp) { done = 1; reason = KSP_DIVERGED_NANORINF; }
+    else if (dp <= scal[S_TTOL]) { done = 1; reason = KSP_CONVERGED_RTOL; }
+    else if (dp >= dtol * scal[S_RNORM0]) { done = 1; reason = KSP_DIVERGED_DTOL; }
+    else if (its >= maxit) { done = 1; reason = KSP_DIVERGED_ITS; }
+    const double beta = rz[1];
+    scal[S_B] = (double)(T)(beta / scal[S_BETAOLD]);
+    scal[S_BETA] = beta;
+    iscal[I_REASON] = reason;
+    if (done) { iscal[I_DONE] = 1; iscal[I_TOTAL] += its; }
+  }
+}
+
+// iteration `it` (1-based): x += a p ; if not converged p = z + b p.
+// Runs iff iteration `it` really executed (it <= I_ITS): the converged iteration still
+// owes x its update (VecAXPY(X,a,P) precedes the test in KSPSolve_CG), a speculative
+// launch past convergence must do nothing.
+template <typename T>
+__global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const double* scal, const int* iscal,
+                            int it) {
+  if (it > iscal[I_ITS]) return;
+  const T a = (T)scal[S_A], b = (T)scal[S_B];
+  const int done = iscal[I_DONE];
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T pv = p[i];
+    x[i] = x[i] + a * pv;
+    if (!done) p[i] = z[i] + b * pv;
+  }
+}
+
+// ---- logistic reaction (src/pde/PdeOperators.cpp:140-190, 318-370) -----------
+// nonlinear: a = c/(1-c); c <- a f/(a f + 1), f = exp(rho dt); c <- 1 if a is inf.
+// `1.0 - c` and `a*f + 1.0` are double expressions in the reference (trap T6).
+template <typename T>
+__global__ void k_reaction(long n, T* c, const T* __restrict__ rho, T dt, T* c_half_out) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T cv = c[i];
+    if (c_half_out) c_half_out[i] = cv;
+    const T factor = g_exp((T)(rho[i] * dt));
+    const T alph = (T)((double)cv / (1.0 - (double)cv));
+    T o;
+    if (g_isinf(alph)) o = (T)1.0;
+    else {
+      const T af = alph * factor;
+      o = (T)((double)af / ((double)af + 1.0));
+    }
+    c[i] = o;
+  }
+}
+// linearised / adjoint: u <- u f / (c f + 1 - c)^2
+template <typename T>
+__global__ void k_reaction_lin(long n, T* u, const T* __restrict__ rho, const T* __restrict__ clin, T dt) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T cv = clin[i];
+    const T factor = g_exp((T)(rho[i] * dt));
+    const T cf = cv * factor;
+    const T alph = (T)(((double)cf + 1.0) - (double)cv);
+    const T uf = u[i] * factor;
+    u[i] = uf / (alph * alph);
+  }
+}
+
+// t = 0.5*(ci + cj) + (first ? ci : cj)   (solveIncremental, src/pde/PdeOperators.cpp:199-226)
+template <typename T>
+__global__ void k_incr_avg(long n, T* t, const T* __restrict__ ci, const T* __restrict__ cj, int first) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    T v = ci[i] + cj[i];
+    v = v * (T)0.5;
+    v = v + (first ? ci[i] : cj[i]);
+    t[i] = v;
+  }
+}
+
+// out = a*x + b*y (y may be null)
+template <typename T>
+__global__ void k_axpby(long n, T* out, T a, const T* x, T b, const T* y) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+
+// partial sums of up to 3 dot products <m_j, t> plus sum(t)
+template <typename T>
+__global__ void k_dot3(long n, const T* __restrict__ t, const T* __restrict__ m0, const T* __restrict__ m1,
+                       const T* __restrict__ m2, double* partial) {
+  double acc[4] = {0, 0, 0, 0};
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double tv = (double)t[i];
+    if (m0) acc[0] += (double)m0[i] * tv;
+    if (m1) acc[1] += (double)m1[i] * tv;
+    if (m2) acc[2] += (double)m2[i] * tv;
+    acc[3] += tv;
+  }
+  // block reduce
+  __shared__ double red[32 * 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  GLIA_UNROLL
+  for (int j = 0; j < 4; ++j) {
+    double v = acc[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid * 4 + j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int w = 0; w < nwarp; ++w) s += red[w * 4 + threadIdx.x];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+  }
+}
+__global__ void k_sum4(const double* partial, int n, double* out) {
+  double o[4];
+  sum_partials<4>(partial, n, o);
+  if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3]; }
+}
+
+}  // namespace glia

@@ -1,0 +1,170 @@
+"""Python host-side mirror of the reference's RD classes over the C ABI.
+
+``RDHandle`` is a thin, pointer-level wrapper of ``glia_rd_t``; the mirror classes in
+``glia_b200.host`` (SpectralOperators, DiffCoef, DiffusionSolver, PdeOperatorsRD,
+DerivativeOperatorsRD) are built on top of it and keep the reference's method names.
+
+Field arguments are anything exposing a device pointer: ``torch`` CUDA tensors
+(``data_ptr()``) in the product, raw ``int`` addresses, or -- only in the emulator tests
+-- NumPy arrays.  All work is done by libglia_rd.so; there is no Python/CPU compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    raise TypeError(f"cannot take a device pointer from {type(x)}")
+
+
+class RDHandle:
+    def __init__(self, n, precision="f32", device=0, dt_ctx=0.5, lib_path=None):
+        self.lib = _capi.load_library(lib_path)
+        self.n = tuple(int(v) for v in (n if hasattr(n, "__len__") else (n, n, n)))
+        self.precision = {"f32": 4, "f64": 8, 4: 4, 8: 8}[precision]
+        self.np_dtype = np.float32 if self.precision == 4 else np.float64
+        self._h = C.c_void_p()
+        arr = (C.c_int * 3)(*self.n)
+        rc = self.lib.glia_rd_create(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx))
+        if rc != 0:
+            msg = self.lib.glia_rd_last_error(self._h).decode() if self._h else "create failed"
+            if self._h:
+                self.lib.glia_rd_destroy(self._h)
+                self._h = C.c_void_p()
+            raise _capi.GliaRdError(msg)
+
+    # -- plumbing ---------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise _capi.GliaRdError(self.lib.glia_rd_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.glia_rd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nreal(self):
+        return self.n[0] * self.n[1] * self.n[2]
+
+    @property
+    def launch_count(self):
+        return int(self.lib.glia_rd_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.glia_rd_stream(self._h)
+
+    # -- L0 -------------------------------------------------------------------------
+    def fft_r2c(self, f, fhat):
+        self._ck(self.lib.glia_rd_fft_r2c(self._h, _ptr(f), _ptr(fhat)))
+
+    def fft_c2r(self, fhat, f):
+        self._ck(self.lib.glia_rd_fft_c2r(self._h, _ptr(fhat), _ptr(f)))
+
+    def gradient(self, gx, gy, gz, x, mask=7):
+        self._ck(self.lib.glia_rd_gradient(self._h, _ptr(gx), _ptr(gy), _ptr(gz), _ptr(x), int(mask)))
+
+    def divergence(self, div, dx, dy, dz):
+        self._ck(self.lib.glia_rd_divergence(self._h, _ptr(div), _ptr(dx), _ptr(dy), _ptr(dz)))
+
+    # -- L1 -------------------------------------------------------------------------
+    def set_diffusion(self, k, kavg, k_scale):
+        ka = (C.c_double * 3)(*[float(v) for v in kavg])
+        self._ck(self.lib.glia_rd_set_diffusion(self._h, _ptr(k), ka, float(k_scale)))
+
+    def set_diffusion_tissue(self, wm, gm, csf, k_scale, k_gm_wm, k_glm_wm, filter_sum):
+        self._ck(self.lib.glia_rd_set_diffusion_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(k_scale),
+                                                       float(k_gm_wm), float(k_glm_wm), float(filter_sum)))
+
+    def set_secondary_k(self, kt):
+        self._ck(self.lib.glia_rd_set_secondary_k(self._h, _ptr(kt)))
+
+    def set_reaction(self, rho):
+        self._ck(self.lib.glia_rd_set_reaction(self._h, _ptr(rho)))
+
+    def set_reaction_tissue(self, wm, gm, csf, rho_scale, r_gm_wm, r_glm_wm):
+        self._ck(self.lib.glia_rd_set_reaction_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(rho_scale),
+                                                      float(r_gm_wm), float(r_glm_wm)))
+
+    def apply_D(self, dc, c, secondary=False):
+        self._ck(self.lib.glia_rd_apply_D(self._h, _ptr(dc), _ptr(c), int(bool(secondary))))
+
+    # -- L2 -------------------------------------------------------------------------
+    def prec_factor(self):
+        self._ck(self.lib.glia_rd_prec_factor(self._h))
+
+    def diffusion_solve(self, c, dt):
+        its = C.c_int(0)
+        self._ck(self.lib.glia_rd_diffusion_solve(self._h, _ptr(c), float(dt), C.byref(its)))
+        return its.value
+
+    def set_ksp_tolerances(self, rtol=1e-6, abstol=1e-50, dtol=1e4, maxit=5000):
+        self._ck(self.lib.glia_rd_set_ksp_tolerances(self._h, rtol, abstol, dtol, int(maxit)))
+
+    # -- L2a ------------------------------------------------------------------------
+    def resize_history(self, nt, dt):
+        self._ck(self.lib.glia_rd_resize_history(self._h, int(nt), float(dt)))
+        self.nt, self.dt = int(nt), float(dt)
+
+    def history_ptr(self, which, i):
+        p = C.c_void_p()
+        self._ck(self.lib.glia_rd_history(self._h, int(which), int(i), C.byref(p)))
+        return p.value
+
+    def reaction(self, c_t, c_lin, dt):
+        self._ck(self.lib.glia_rd_reaction(self._h, _ptr(c_t), _ptr(c_lin), float(dt)))
+
+    def solve_state(self, c0, cT=None, linearized=0):
+        its = C.c_int(0)
+        self._ck(self.lib.glia_rd_solve_state(self._h, _ptr(c0), _ptr(cT), int(linearized), C.byref(its)))
+        return its.value
+
+    def solve_adjoint(self, pT, p0=None, linearized=1, adjoint_store=True):
+        its = C.c_int(0)
+        self._ck(self.lib.glia_rd_solve_adjoint(self._h, _ptr(pT), _ptr(p0), int(linearized),
+                                                int(bool(adjoint_store)), C.byref(its)))
+        return its.value
+
+    # -- L2b ------------------------------------------------------------------------
+    def grad_kappa_rho(self, wm, gm, csf):
+        out = (C.c_double * 6)()
+        self._ck(self.lib.glia_rd_grad_kappa_rho(self._h, _ptr(wm), _ptr(gm), _ptr(csf), out))
+        return np.array(list(out))
+
+    # -- timing / host entry ---------------------------------------------------------
+    def timer_start(self):
+        self._ck(self.lib.glia_rd_timer_start(self._h))
+
+    def timer_stop_ms(self):
+        ms = C.c_double(0)
+        self._ck(self.lib.glia_rd_timer_stop_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def forward_adjoint_host(self, c0, d1, cT, p0):
+        """Host-buffer (NumPy) end-to-end call: H2D, forward, adjoint, D2H inside."""
+        for a in (c0, d1, cT, p0):
+            assert isinstance(a, np.ndarray) and a.dtype == self.np_dtype and a.flags["C_CONTIGUOUS"]
+        ks, ka = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.glia_rd_forward_adjoint_host(self._h, c0.ctypes.data, d1.ctypes.data, cT.ctypes.data,
+                                                       p0.ctypes.data, C.byref(ks), C.byref(ka)))
+        return ks.value, ka.value

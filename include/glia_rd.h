@@ -1,0 +1,132 @@
+/* glia_rd.h -- C ABI of libglia_rd.so: the B200-native (sm_100a) replacement for the
+ * CUDA seam of GLIA's reaction-diffusion forward/adjoint hot path.
+ *
+ * The reference has no plugin / FFI layer: its seam is the `#ifdef CUDA` blocks inside
+ * SpectralOperators, DiffCoef, DiffusionSolver and PdeOperatorsRD, which call free
+ * functions on raw device pointers borrowed from PETSc Vecs (vecGetArray,
+ * src/utils/Utils.cpp:69-93).  Each entry point below names the reference method it
+ * replaces (paths relative to the GLIA repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (never exits the process,
+ *     mirroring PetscErrorCode); glia_rd_last_error() returns the message;
+ *   - `void*` field arguments are DEVICE pointers to `float` (precision 4) or `double`
+ *     (precision 8) in the PETSc-Vec layout of the reference: C order [n0][n1][n2], z
+ *     fastest (src/mat/DiffCoef.cpp:150); they stay owned by the caller;
+ *   - calls are enqueued on the handle's stream and are synchronous at return;
+ *   - a handle is not thread-safe; one handle per (process, device).
+ */
+#ifndef GLIA_RD_H
+#define GLIA_RD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct glia_rd glia_rd_t;
+
+#define GLIA_RD_F32 4
+#define GLIA_RD_F64 8
+
+/* history selectors for glia_rd_history() */
+#define GLIA_HIST_C 0      /* c_[i],      i = 0..nt   (include/pde/PdeOperators.h) */
+#define GLIA_HIST_P 1      /* p_[i],      i = 0..nt   */
+#define GLIA_HIST_C_HALF 2 /* c_half_[i], i = 0..nt-1 */
+
+/* Library / ABI version and build flavour ("cuda-sm_100a"). */
+int glia_rd_abi_version(void);
+const char* glia_rd_build_info(void);
+
+/* Grid + plan set-up.  Replaces SpectralOperators::setup / initializeGrid
+ * (src/grad/SpectralOperators.cpp:19-66, 424-446).  n[i] must be a power of two in
+ * [32, 512].  `device` is the CUDA ordinal.  dt_ctx initialises the diffusion solver's
+ * context time step exactly like params->tu_->dt_ does in the DiffusionSolver ctor
+ * (src/pde/DiffusionSolver.cpp:11); pass 0.5 for the reference default. */
+int glia_rd_create(glia_rd_t** h, const int n[3], int precision, int device, double dt_ctx);
+int glia_rd_destroy(glia_rd_t* h);
+const char* glia_rd_last_error(const glia_rd_t* h);
+/* the CUDA stream (cudaStream_t) all work of this handle is enqueued on */
+void* glia_rd_stream(glia_rd_t* h);
+/* number of kernel launches issued by this handle since creation */
+long long glia_rd_launch_count(const glia_rd_t* h);
+
+/* ---- L0: SpectralOperators ------------------------------------------------------- */
+/* executeFFTR2C / executeFFTC2R (src/grad/SpectralOperators.cpp:68-98): unnormalised,
+ * fhat is [n0][n1][n2/2+1] interleaved complex. */
+int glia_rd_fft_r2c(glia_rd_t* h, const void* f, void* fhat);
+int glia_rd_fft_c2r(glia_rd_t* h, const void* fhat, void* f);
+/* computeGradient (SpectralOperators.cpp:100-177); xyz_mask bit0=x, bit1=y, bit2=z;
+ * unrequested components may be NULL. */
+int glia_rd_gradient(glia_rd_t* h, void* gx, void* gy, void* gz, const void* x, int xyz_mask);
+/* computeDivergence (SpectralOperators.cpp:179-261). */
+int glia_rd_divergence(glia_rd_t* h, void* div, const void* dx, const void* dy, const void* dz);
+
+/* ---- L1: DiffCoef / ReacCoef ------------------------------------------------------ */
+/* Isotropic diffusion coefficient field kxx=kyy=kzz=k and its three preconditioner
+ * averages (kxx_avg_, kyy_avg_, kzz_avg_; DiffCoef.cpp:103-116).  The field is copied.
+ * k_scale is DiffCoef::k_scale_ (solve() returns immediately when it is 0,
+ * DiffusionSolver.cpp:227). */
+int glia_rd_set_diffusion(glia_rd_t* h, const void* k, const double kavg[3], double k_scale);
+/* DiffCoef::setValues (DiffCoef.cpp:77-131): k = k_scale*(wm + k_gm_wm*gm + k_glm_wm*csf),
+ * negative ratios clamp to 0; averages = sum(k)/filter_sum (filter_sum = sum of the
+ * brain mask, MatProp.cpp:180-185; pass n0*n1*n2 for setValuesSinusoidal semantics). */
+int glia_rd_set_diffusion_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf,
+                                 double k_scale, double k_gm_wm, double k_glm_wm, double filter_sum);
+/* DiffCoef::setSecondaryCoefficients (DiffCoef.cpp:44-59): ktilde field (copied). */
+int glia_rd_set_secondary_k(glia_rd_t* h, const void* ktilde);
+/* ReacCoef::rho_vec_ (src/mat/ReacCoef.cpp:13-38); the field is copied. */
+int glia_rd_set_reaction(glia_rd_t* h, const void* rho);
+int glia_rd_set_reaction_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf,
+                                double rho_scale, double r_gm_wm, double r_glm_wm);
+/* DiffCoef::applyD / applyDWithSecondaryCoeffs (DiffCoef.cpp:249-300); dc may alias c. */
+int glia_rd_apply_D(glia_rd_t* h, void* dc, const void* c, int secondary);
+
+/* ---- L2: DiffusionSolver ---------------------------------------------------------- */
+/* DiffusionSolver::precFactor (DiffusionSolver.cpp:119-180): freezes the preconditioner
+ * symbol from the CURRENT context dt and averages (the stale-dt behaviour of the
+ * reference is state and is reproduced on purpose). */
+int glia_rd_prec_factor(glia_rd_t* h);
+/* DiffusionSolver::solve(c, dt) (DiffusionSolver.cpp:217-250): Crank-Nicolson step by
+ * PETSc-semantics preconditioned CG (rtol 1e-6, abstol 1e-50, maxit 5000, non-zero
+ * initial guess, preconditioned norm).  c is updated in place; *ksp_its = ksp_itr_. */
+int glia_rd_diffusion_solve(glia_rd_t* h, void* c, double dt, int* ksp_its);
+int glia_rd_set_ksp_tolerances(glia_rd_t* h, double rtol, double abstol, double dtol, int maxit);
+
+/* ---- L2a: PdeOperatorsRD ----------------------------------------------------------- */
+/* PdeOperatorsRD ctor / resizeTimeHistory (src/pde/PdeOperators.cpp:17-103):
+ * (nt+1) state + (nt+1) adjoint + nt half-step fields, zero-initialised. */
+int glia_rd_resize_history(glia_rd_t* h, int nt, double dt);
+int glia_rd_history(glia_rd_t* h, int which, int i, void** dev_ptr);
+/* PdeOperatorsRD::reaction (PdeOperators.cpp:140-190): c_lin == NULL -> nonlinear
+ * logistic step, else the linearised step about c_lin. */
+int glia_rd_reaction(glia_rd_t* h, void* c_t, const void* c_lin, double dt);
+/* PdeOperatorsRD::solveState(linearized) (PdeOperators.cpp:235-316).  c0 -> cT (may be
+ * NULL); linearized 0/1/2; *ksp_its_total = diff_ksp_itr_state_. */
+int glia_rd_solve_state(glia_rd_t* h, const void* c0, void* cT, int linearized, int* ksp_its_total);
+/* PdeOperatorsRD::solveAdjoint(linearized) (PdeOperators.cpp:372-420).  pT -> p0 (may be
+ * NULL); adjoint_store selects c_half_ (1) or the re-diffusion of c_[k] (0). */
+int glia_rd_solve_adjoint(glia_rd_t* h, const void* pT, void* p0, int linearized, int adjoint_store,
+                          int* ksp_its_total);
+
+/* ---- L2b: gradient time integrals -------------------------------------------------- */
+/* DerivativeOperators::gradDiffusion + gradReaction (src/grad/DerivativeOperators.cpp:
+ * 189-321): out = h^3 * { <wm,Tk>, <gm,Tk>, <csf,Tk>, <wm,Tr>, <gm,Tr>, <csf,Tr> } with
+ * Tk = sum_i w_i dt grad c_i . grad p_i, Tr = sum_i w_i dt p_i (c_i^2 - c_i) over the
+ * stored histories (trapezoid weights).  The same call serves the Hkp / Hkk integrals of
+ * evaluateHessian (DerivativeOperatorsRD.cpp:270-320, 355-407). */
+int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double out[6]);
+
+/* ---- timing helper (CUDA events on the handle's stream) --------------------------- */
+int glia_rd_timer_start(glia_rd_t* h);
+int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms);
+
+/* ---- host-buffer convenience (plugin-style end-to-end call, H2D/D2H inside) -------- */
+/* One forward + adjoint solve with HOST buffers: c0 (in), d1 (data, in), cT (out),
+ * p0 (out); adjoint terminal condition -(c(T) - d1) (O = I).  Used for bench `e2e`. */
+int glia_rd_forward_adjoint_host(glia_rd_t* h, const void* c0_host, const void* d1_host, void* cT_host,
+                                 void* p0_host, int* ksp_state, int* ksp_adj);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIA_RD_H */
