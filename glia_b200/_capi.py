@@ -45,6 +45,8 @@ SIGNATURES = {
     "glia_rd_solve_state": (_I, [_P, _P, _P, _I, C.POINTER(_I)]),
     "glia_rd_solve_adjoint": (_I, [_P, _P, _P, _I, _I, C.POINTER(_I)]),
     "glia_rd_grad_kappa_rho": (_I, [_P, _P, _P, _P, C.POINTER(_D)]),
+    "glia_rd_profile_begin": (_I, [_P]),
+    "glia_rd_profile_end": (_I, [_P, C.c_char_p, _I]),
     "glia_rd_timer_start": (_I, [_P]),
     "glia_rd_timer_stop_ms": (_I, [_P, C.POINTER(_D)]),
     "glia_rd_forward_adjoint_host": (_I, [_P, _P, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
@@ -80,4 +82,4 @@ def declared_symbols(header_path: str) -> list[str]:
     import re
     txt = open(header_path).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(glia_rd_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(glia_rd_[A-Za-z0-9_]+)\s*\(", txt)))

@@ -1,8 +1,12 @@
-// c_api.cu -- extern "C" surface of libglia_rd (see include/glia_rd.h).
+// c_api.cu -- extern "C" surface of libglia_rd (see include/glia_rd.h).  Everything here is
+// argument checking and error translation; the work is in Engine<T> (engine.cuh).
 #include "../../include/glia_rd.h"
 
-#include "engine.cuh"
-#include "spectral3d.cuh"
+#include "engine_base.h"
+#include <cstring>
+#if !defined(GLIA_SIMT_EMU)
+#include <cuda_runtime.h>
+#endif
 
 using namespace glia;
 
@@ -14,9 +18,10 @@ struct glia_rd {
 namespace {
 template <class F>
 int guarded(glia_rd_t* h, F f) {
-  if (!h || !h->eng) return 2;
+  if (!h) return 2;
+  if (!h->eng) { h->err = "handle has no engine (creation failed)"; return 2; }
   try {
-    f();
+    f(*h->eng);
     return 0;
   } catch (const EngineError& e) {
     h->err = e.msg;
@@ -26,11 +31,6 @@ int guarded(glia_rd_t* h, F f) {
     return 1;
   }
 }
-#define WITH_ENGINE(h, body)                                                  \
-  guarded(h, [&]() {                                                          \
-    if (h->eng->precision() == 4) { auto& E = *static_cast<Engine<float>*>(h->eng); using T = float; (void)sizeof(T); body; } \
-    else { auto& E = *static_cast<Engine<double>*>(h->eng); using T = double; (void)sizeof(T); body; }                      \
-  })
 }  // namespace
 
 extern "C" {
@@ -48,6 +48,7 @@ int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, d
   if (!out) return 2;
   *out = nullptr;
   glia_rd_t* h = new glia_rd();
+  *out = h;  // also on failure, so that the caller can read the message
   try {
 #if !defined(GLIA_SIMT_EMU)
     int ndev = 0;
@@ -55,16 +56,19 @@ int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, d
       cudaGetLastError();
       throw EngineError{"no CUDA device: libglia_rd has no CPU fallback"};
     }
+    if (device < 0 || device >= ndev) throw EngineError{"device ordinal out of range"};
 #endif
-    if (precision == GLIA_RD_F32) h->eng = new Engine<float>(n, device, dt_ctx);
-    else if (precision == GLIA_RD_F64) h->eng = new Engine<double>(n, device, dt_ctx);
+    if (!n) throw EngineError{"n is null"};
+    if (precision == GLIA_RD_F32) h->eng = make_engine_f32(n, device, dt_ctx);
+    else if (precision == GLIA_RD_F64) h->eng = make_engine_f64(n, device, dt_ctx);
     else throw EngineError{"precision must be 4 or 8"};
   } catch (const EngineError& e) {
     h->err = e.msg;
-    *out = h;  // so the caller can read the message
+    return 1;
+  } catch (const std::exception& e) {
+    h->err = e.what();
     return 1;
   }
-  *out = h;
   return 0;
 }
 int glia_rd_destroy(glia_rd_t* h) {
@@ -74,82 +78,108 @@ int glia_rd_destroy(glia_rd_t* h) {
   return 0;
 }
 const char* glia_rd_last_error(const glia_rd_t* h) { return h ? h->err.c_str() : "null handle"; }
-void* glia_rd_stream(glia_rd_t* h) {
-  if (!h || !h->eng) return nullptr;
-  if (h->eng->precision() == 4) return (void*)(intptr_t) static_cast<Engine<float>*>(h->eng)->st;
-  return (void*)(intptr_t) static_cast<Engine<double>*>(h->eng)->st;
-}
+void* glia_rd_stream(glia_rd_t* h) { return (h && h->eng) ? h->eng->stream_handle() : nullptr; }
 long long glia_rd_launch_count(const glia_rd_t* h) { return (h && h->eng) ? h->eng->launches : 0; }
 
 int glia_rd_fft_r2c(glia_rd_t* h, const void* f, void* fhat) {
-  return WITH_ENGINE(h, fft3d_r2c(E, (const T*)f, (cplx<T>*)fhat));
+  return guarded(h, [&](EngineBase& E) { E.v_fft_r2c(f, fhat); });
 }
 int glia_rd_fft_c2r(glia_rd_t* h, const void* fhat, void* f) {
-  return WITH_ENGINE(h, fft3d_c2r(E, (const cplx<T>*)fhat, (T*)f));
+  return guarded(h, [&](EngineBase& E) { E.v_fft_c2r(fhat, f); });
 }
 int glia_rd_gradient(glia_rd_t* h, void* gx, void* gy, void* gz, const void* x, int m) {
-  return WITH_ENGINE(h, E.gradient((T*)gx, (T*)gy, (T*)gz, (const T*)x, m));
+  return guarded(h, [&](EngineBase& E) { E.v_gradient(gx, gy, gz, x, m); });
 }
 int glia_rd_divergence(glia_rd_t* h, void* div, const void* dx, const void* dy, const void* dz) {
-  return WITH_ENGINE(h, E.divergence((T*)div, (const T*)dx, (const T*)dy, (const T*)dz));
+  return guarded(h, [&](EngineBase& E) { E.v_divergence(div, dx, dy, dz); });
 }
 int glia_rd_set_diffusion(glia_rd_t* h, const void* k, const double kavg[3], double k_scale) {
-  return WITH_ENGINE(h, E.set_diffusion((const T*)k, kavg, k_scale));
+  return guarded(h, [&](EngineBase& E) { E.v_set_diffusion(k, kavg, k_scale); });
 }
 int glia_rd_set_diffusion_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double ks,
                                  double kgm, double kglm, double fsum) {
-  return WITH_ENGINE(h, E.set_diffusion_tissue((const T*)wm, (const T*)gm, (const T*)csf, ks, kgm, kglm, fsum));
+  return guarded(h, [&](EngineBase& E) { E.v_set_diffusion_tissue(wm, gm, csf, ks, kgm, kglm, fsum); });
 }
 int glia_rd_set_secondary_k(glia_rd_t* h, const void* kt) {
-  return WITH_ENGINE(h, { GLIA_CHECK(rt::copy(E.ktil, kt, sizeof(T) * E.nreal, E.st)); E.sync(); });
+  return guarded(h, [&](EngineBase& E) { E.v_set_secondary_k(kt); });
 }
 int glia_rd_set_reaction(glia_rd_t* h, const void* rho) {
-  return WITH_ENGINE(h, { GLIA_CHECK(rt::copy(E.rho, rho, sizeof(T) * E.nreal, E.st)); E.sync(); });
+  return guarded(h, [&](EngineBase& E) { E.v_set_reaction(rho); });
 }
 int glia_rd_set_reaction_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double rs, double rgm,
                                 double rglm) {
-  return WITH_ENGINE(h, E.set_reaction_tissue((const T*)wm, (const T*)gm, (const T*)csf, rs, rgm, rglm));
+  return guarded(h, [&](EngineBase& E) { E.v_set_reaction_tissue(wm, gm, csf, rs, rgm, rglm); });
 }
 int glia_rd_apply_D(glia_rd_t* h, void* dc, const void* c, int secondary) {
-  return WITH_ENGINE(h, E.apply_D((T*)dc, (const T*)c, secondary != 0));
+  return guarded(h, [&](EngineBase& E) { E.v_apply_D(dc, c, secondary); });
 }
-int glia_rd_prec_factor(glia_rd_t* h) { return WITH_ENGINE(h, E.prec_factor()); }
+int glia_rd_prec_factor(glia_rd_t* h) {
+  return guarded(h, [&](EngineBase& E) { E.v_prec_factor(); });
+}
 int glia_rd_diffusion_solve(glia_rd_t* h, void* c, double dt, int* its) {
-  return WITH_ENGINE(h, {
-    int k = E.diffusion_solve((T*)c, dt);
-    E.sync();
+  return guarded(h, [&](EngineBase& E) {
+    const int k = E.v_diffusion_solve(c, dt);
     if (its) *its = k;
   });
 }
 int glia_rd_set_ksp_tolerances(glia_rd_t* h, double rtol, double abstol, double dtol, int maxit) {
-  return WITH_ENGINE(h, { E.rtol = rtol; E.abstol = abstol; E.dtol = dtol; E.maxit = maxit; });
+  return guarded(h, [&](EngineBase& E) { E.v_set_ksp_tolerances(rtol, abstol, dtol, maxit); });
 }
-int glia_rd_resize_history(glia_rd_t* h, int nt, double dt) { return WITH_ENGINE(h, E.resize_history(nt, dt)); }
+int glia_rd_resize_history(glia_rd_t* h, int nt, double dt) {
+  return guarded(h, [&](EngineBase& E) { E.v_resize_history(nt, dt); });
+}
 int glia_rd_history(glia_rd_t* h, int which, int i, void** p) {
-  return WITH_ENGINE(h, { *p = (void*)E.hist(which, i); });
+  return guarded(h, [&](EngineBase& E) {
+    if (!p) throw EngineError{"null output pointer"};
+    *p = E.v_history(which, i);
+  });
 }
 int glia_rd_reaction(glia_rd_t* h, void* ct, const void* clin, double dt) {
-  return WITH_ENGINE(h, { E.reaction((T*)ct, (const T*)clin, (T)dt, nullptr); E.sync(); });
+  return guarded(h, [&](EngineBase& E) { E.v_reaction(ct, clin, dt); });
 }
 int glia_rd_solve_state(glia_rd_t* h, const void* c0, void* cT, int lin, int* its) {
-  return WITH_ENGINE(h, {
-    int k = E.solve_state((const T*)c0, (T*)cT, lin);
+  return guarded(h, [&](EngineBase& E) {
+    const int k = E.v_solve_state(c0, cT, lin);
     if (its) *its = k;
   });
 }
 int glia_rd_solve_adjoint(glia_rd_t* h, const void* pT, void* p0, int lin, int store, int* its) {
-  return WITH_ENGINE(h, {
-    int k = E.solve_adjoint((const T*)pT, (T*)p0, lin, store);
+  return guarded(h, [&](EngineBase& E) {
+    const int k = E.v_solve_adjoint(pT, p0, lin, store);
     if (its) *its = k;
   });
 }
 int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double out[6]) {
-  return WITH_ENGINE(h, E.grad_kappa_rho((const T*)wm, (const T*)gm, (const T*)csf, out));
+  return guarded(h, [&](EngineBase& E) { E.v_grad_kappa_rho(wm, gm, csf, out); });
 }
-int glia_rd_timer_start(glia_rd_t* h) { return WITH_ENGINE(h, E.timer.start(E.st)); }
-int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms) { return WITH_ENGINE(h, { *ms = E.timer.stop_ms(E.st); }); }
+int glia_rd_profile_begin(glia_rd_t* h) {
+  return guarded(h, [&](EngineBase& E) { E.v_profile_begin(); });
+}
+int glia_rd_profile_end(glia_rd_t* h, char* buf, int buflen) {
+  return guarded(h, [&](EngineBase& E) {
+    const std::string s = E.v_profile_end();
+    if (buf && buflen > 0) {
+      std::strncpy(buf, s.c_str(), (size_t)buflen - 1);
+      buf[buflen - 1] = 0;
+    }
+  });
+}
+int glia_rd_timer_start(glia_rd_t* h) {
+  return guarded(h, [&](EngineBase& E) { E.v_timer_start(); });
+}
+int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms) {
+  return guarded(h, [&](EngineBase& E) {
+    const double t = E.v_timer_stop_ms();
+    if (ms) *ms = t;
+  });
+}
 int glia_rd_forward_adjoint_host(glia_rd_t* h, const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) {
-  return WITH_ENGINE(h, E.forward_adjoint_host((const T*)c0, (const T*)d1, (T*)cT, (T*)p0, ks, ka));
+  return guarded(h, [&](EngineBase& E) {
+    int a = 0, b = 0;
+    E.v_forward_adjoint_host(c0, d1, cT, p0, &a, &b);
+    if (ks) *ks = a;
+    if (ka) *ka = b;
+  });
 }
 
 }  // extern "C"

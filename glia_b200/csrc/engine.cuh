@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "engine_base.h"
 #include "pointwise.cuh"
 #include "sweeps.cuh"
 
@@ -15,22 +16,7 @@ namespace glia {
 
 // ------------------------------------------------------------------ runtime ----
 namespace rt {
-#if defined(GLIA_SIMT_EMU)
-inline int dev_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 1; }
-inline void dev_free(void* p) { std::free(p); }
-inline int host_malloc(void** p, size_t n) { return dev_malloc(p, n); }
-inline void host_free(void* p) { std::free(p); }
-inline int copy(void* d, const void* s, size_t n, cudaStream_t) { std::memmove(d, s, n); return 0; }
-inline int h2d(void* d, const void* s, size_t n, cudaStream_t st) { return copy(d, s, n, st); }
-inline int d2h(void* d, const void* s, size_t n, cudaStream_t st) { return copy(d, s, n, st); }
-inline int zero(void* d, size_t n, cudaStream_t) { std::memset(d, 0, n); return 0; }
-inline int sync(cudaStream_t) { return 0; }
-inline int set_device(int) { return 0; }
-inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
-inline void stream_destroy(cudaStream_t) {}
-inline const char* err_string(int) { return "emu"; }
-struct Timer { void create() {} void destroy() {} void start(cudaStream_t) {} double stop_ms(cudaStream_t) { return 0; } };
-#else
+#if !defined(GLIA_SIMT_EMU)  // the emulator build supplies rt:: from tests/emu/simt_emu.h
 inline int dev_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
 inline int host_malloc(void** p, size_t n) { return (int)cudaMallocHost(p, n ? n : 1); }
@@ -44,6 +30,49 @@ inline int set_device(int d) { return (int)cudaSetDevice(d); }
 inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
+// per-launch CUDA-event profiler (off by default: zero overhead besides one branch)
+struct Profiler {
+  struct Rec { const char* tag; cudaEvent_t a, b; };
+  bool on = false;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+  int before(const char* tag, cudaStream_t s) {
+    if (!on) return -1;
+    Rec r{tag, get(), get()};
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+    return (int)recs.size() - 1;
+  }
+  void after(int slot, cudaStream_t s) { if (slot >= 0) cudaEventRecord(recs[slot].b, s); }
+  void begin() { recs.clear(); used = 0; on = true; }
+  // aggregate by tag: "tag count total_ms\n" lines
+  std::string end(cudaStream_t s) {
+    on = false;
+    cudaStreamSynchronize(s);
+    std::vector<std::string> names; std::vector<double> tot; std::vector<long> cnt;
+    for (auto& r : recs) {
+      float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      size_t i = 0;
+      for (; i < names.size(); ++i) if (names[i] == r.tag) break;
+      if (i == names.size()) { names.push_back(r.tag); tot.push_back(0); cnt.push_back(0); }
+      tot[i] += ms; cnt[i]++;
+    }
+    std::string out;
+    char buf[256];
+    for (size_t i = 0; i < names.size(); ++i) {
+      std::snprintf(buf, sizeof buf, "%s %ld %.6f\n", names[i].c_str(), cnt[i], tot[i]);
+      out += buf;
+    }
+    recs.clear(); used = 0;
+    return out;
+  }
+  void destroy() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   void create() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -60,9 +89,6 @@ struct Timer {
 #endif
 }  // namespace rt
 
-struct EngineError {
-  std::string msg;
-};
 
 #define GLIA_CHECK(expr)                                                                       \
   do {                                                                                         \
@@ -80,13 +106,10 @@ struct EngineError {
     default: throw EngineError{"unsupported line length " + std::to_string(nval)}; \
   }
 
-class EngineBase {
- public:
-  virtual ~EngineBase() {}
-  std::string last_error;
-  long long launches = 0;
-  virtual int precision() const = 0;
-};
+
+template <typename T> class Engine;
+template <typename T> void fft3d_r2c(Engine<T>& E, const T* f, cplx<T>* fhat);
+template <typename T> void fft3d_c2r(Engine<T>& E, const cplx<T>* fhat, T* f);
 
 template <typename T>
 class Engine : public EngineBase {
@@ -97,6 +120,7 @@ class Engine : public EngineBase {
   int n2c;  // n2/2: complex columns of the pair view
   cudaStream_t st = 0;
   rt::Timer timer;
+  rt::Profiler prof;
 
   // coefficients
   T *kf = nullptr, *ktil = nullptr, *rho = nullptr;
@@ -178,9 +202,20 @@ class Engine : public EngineBase {
     rt::host_free(h_iscal); rt::host_free(h_out);
     rt::host_free(hs_in); rt::host_free(hs_out);
     timer.destroy();
+    prof.destroy();
     rt::stream_destroy(st);
   }
 
+  // every kernel launch of the engine goes through here: counted, and (when profiling is on)
+  // bracketed by CUDA events on the engine's stream so that bench.py can report each kernel's
+  // average duration live.
+  template <class... KA, class... A>
+  void L(const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
+    const int slot = prof.before(tag, s);
+    simt::launch(k, g, b, smem, s, args...);
+    prof.after(slot, s);
+    ++launches;
+  }
   void check_launch() {
     const char* e = simt::last_error();
     if (e) throw EngineError{std::string("kernel launch: ") + e};
@@ -210,16 +245,15 @@ class Engine : public EngineBase {
   // acc = Dz(k Dz x); acc += Dy(k Dy x); then the x sweep with epilogue EPI
   template <int EPI>
   int dapply(const T* x, const T* kfield, T alpha, T* out1, T* out2, double* pp, const int* done) {
-    GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+    GLIA_DISPATCH_N(n[2], L("kz_deriv2", kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                        lines_z(), x, kfield, acc, (const C*)tw[2], done));
     const TileS ty = tile_y(), tx = tile_x();
-    GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], L("ks_deriv2.y", ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[1], (T)0, (C*)nullptr,
                                        (C*)nullptr, (double*)nullptr, done));
-    GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+    GLIA_DISPATCH_N(n[0], L("ks_deriv2.x", ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                        (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[0], alpha, (C*)out1,
                                        (C*)out2, pp, done));
-    launches += 3;
     return (int)grid_s(tx).x;
   }
 
@@ -228,25 +262,24 @@ class Engine : public EngineBase {
     const TileS ty = tile_y(), tx = tile_x();
     int nblk = 0;
     if (wv) {
-      GLIA_DISPATCH_N(n[2], simt::launch(kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], L("kz_r2c", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done));
     } else {
-      GLIA_DISPATCH_N(n[2], simt::launch(kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], L("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
                                          (const C*)tw[2], done));
     }
-    GLIA_DISPATCH_N(n[1], simt::launch(ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
-    GLIA_DISPATCH_N(n[0], simt::launch(ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
+    GLIA_DISPATCH_N(n[0], L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
                                        (const C*)tw[0], sym, n[1], done));
-    GLIA_DISPATCH_N(n[1], simt::launch(ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
     GLIA_DISPATCH_N(n[2], {
       nblk = (int)grid_z<N>().x;
-      simt::launch(kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
+      L("kz_c2r", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
                    zout, want_rz ? (const T*)rin : (const T*)nullptr, pp, (const C*)tw[2], done);
     });
-    launches += 5;
     return nblk;
   }
 
@@ -254,31 +287,27 @@ class Engine : public EngineBase {
   void gradient(T* gx, T* gy, T* gz, const T* x, int mask) {
     const TileS ty = tile_y(), tx = tile_x();
     if ((mask & 4) && gz) {
-      GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], L("kz_deriv1", kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), x, gz, (const C*)tw[2]));
-      launches++;
     }
     if ((mask & 2) && gy) {
-      GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv1<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+      GLIA_DISPATCH_N(n[1], L("ks_deriv1.y", ks_deriv1<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                          (const C*)x, (C*)gy, (const C*)tw[1]));
-      launches++;
     }
     if ((mask & 1) && gx) {
-      GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv1<T, N, 0>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+      GLIA_DISPATCH_N(n[0], L("ks_deriv1.x", ks_deriv1<T, N, 0>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                          (const C*)x, (C*)gx, (const C*)tw[0]));
-      launches++;
     }
     sync();
   }
   void divergence(T* div, const T* dx, const T* dy, const T* dz) {
     const TileS ty = tile_y(), tx = tile_x();
-    GLIA_DISPATCH_N(n[2], simt::launch(kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+    GLIA_DISPATCH_N(n[2], L("kz_deriv1", kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                        lines_z(), dz, div, (const C*)tw[2]));
-    GLIA_DISPATCH_N(n[1], simt::launch(ks_deriv1<T, N, 1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], L("ks_deriv1.y", ks_deriv1<T, N, 1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)dy, (C*)div, (const C*)tw[1]));
-    GLIA_DISPATCH_N(n[0], simt::launch(ks_deriv1<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+    GLIA_DISPATCH_N(n[0], L("ks_deriv1.x", ks_deriv1<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                        (const C*)dx, (C*)div, (const C*)tw[0]));
-    launches += 3;
     sync();
   }
 
@@ -291,9 +320,8 @@ class Engine : public EngineBase {
   }
   void field_sum4(const T* t, const T* m0, const T* m1, const T* m2, double out[4]) {
     const dim3 g = grid_pw(nreal);
-    simt::launch(k_dot3<T>, g, dim3(256), 0, st, nreal, t, m0, m1, m2, part(0));
-    simt::launch(k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8);
-    launches += 2;
+    L("k_dot3", k_dot3<T>, g, dim3(256), 0, st, nreal, t, m0, m1, m2, part(0));
+    L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8);
     GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
     sync();
     for (int i = 0; i < 4; ++i) out[i] = h_out[i];
@@ -307,10 +335,9 @@ class Engine : public EngineBase {
     if (dk_glm <= 0) dk_glm = 0;
     const dim3 g = grid_pw(nreal);
     // kxx = 0; kxx += dk_gm*gm; kxx += dk_wm*wm; kxx += dk_glm*csf
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_gm, gm, (T)0, (const T*)nullptr);
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_wm, wm, (T)1, (const T*)kf);
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_glm, csf, (T)1, (const T*)kf);
-    launches += 3;
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_gm, gm, (T)0, (const T*)nullptr);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_wm, wm, (T)1, (const T*)kf);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, kf, dk_glm, csf, (T)1, (const T*)kf);
     double s[4];
     field_sum4(kf, nullptr, nullptr, nullptr, s);
     const T ksum = (T)s[3];
@@ -323,10 +350,9 @@ class Engine : public EngineBase {
     if (dr_gm <= 0) dr_gm = 0;
     if (dr_glm <= 0) dr_glm = 0;
     const dim3 g = grid_pw(nreal);
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_gm, gm, (T)0, (const T*)nullptr);
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_wm, wm, (T)1, (const T*)rho);
-    simt::launch(k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_glm, csf, (T)1, (const T*)rho);
-    launches += 3;
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_gm, gm, (T)0, (const T*)nullptr);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_wm, wm, (T)1, (const T*)rho);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_glm, csf, (T)1, (const T*)rho);
     sync();
   }
   void apply_D(T* dc, const T* c, bool secondary) {
@@ -357,12 +383,11 @@ class Engine : public EngineBase {
     const int* done = iscal + I_DONE;
     const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
     const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
-    simt::launch(k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal);
+    L("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal);
     const int nb2 = pc_apply(r, w, z, true, part(1), done);
-    simt::launch(k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol);
-    simt::launch(k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
+    L("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol);
+    L("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
                  (const int*)iscal, it);
-    launches += 3;
   }
 
   // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.
@@ -374,9 +399,8 @@ class Engine : public EngineBase {
     dapply<EPI_RHS>(x, kf, alph, b, r, nullptr, nullptr);
     const int nb0 = pc_apply(b, nullptr, nullptr, false, part(2), nullptr);
     const int nb1 = pc_apply(r, nullptr, p, true, part(1), nullptr);
-    simt::launch(k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
+    L("k_pcg_init", k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
                  scal, iscal, rtol, abstol);
-    launches++;
     int it = 0;
     // speculate: enqueue as many iterations as the previous solve needed, then look
     int burst = its_guess < 1 ? 1 : its_guess;
@@ -417,16 +441,14 @@ class Engine : public EngineBase {
   }
   void reaction(T* ct, const T* clin, T dtr, T* chalf_out) {
     if (clin)
-      simt::launch(k_reaction_lin<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, clin, dtr);
+      L("k_reaction_lin", k_reaction_lin<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, clin, dtr);
     else
-      simt::launch(k_reaction<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, dtr, chalf_out);
-    launches++;
+      L("k_reaction", k_reaction<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, dtr, chalf_out);
   }
   // PdeOperatorsRD::solveIncremental
   void solve_incremental(T* ctil, int i, int mode, T dth) {
-    simt::launch(k_incr_avg<T>, grid_pw(nreal), dim3(256), 0, st, nreal, work11, (const T*)hist(0, i),
+    L("k_incr_avg", k_incr_avg<T>, grid_pw(nreal), dim3(256), 0, st, nreal, work11, (const T*)hist(0, i),
                  (const T*)hist(0, i + 1), mode == 1 ? 1 : 0);
-    launches++;
     // c_tilde += dt/2 * D~ temp   (caller passes dt/2, the update uses dt/2 of that)
     dapply<EPI_AXPY>(work11, ktil, (T)(dth / 2), ctil, nullptr, nullptr, nullptr);
   }
@@ -484,13 +506,12 @@ class Engine : public EngineBase {
       const T coef = dt * wgt;
       const T* ci = hist(0, i);
       const T* pi = hist(1, i);
-      GLIA_DISPATCH_N(n[2], simt::launch(kz_gradprod<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], L("kz_gradprod", kz_gradprod<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), ci, pi, Tk, Tr, coef, (const C*)tw[2]));
-      GLIA_DISPATCH_N(n[1], simt::launch(ks_gradprod<T, N>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+      GLIA_DISPATCH_N(n[1], L("ks_gradprod.y", ks_gradprod<T, N>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                          (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[1]));
-      GLIA_DISPATCH_N(n[0], simt::launch(ks_gradprod<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+      GLIA_DISPATCH_N(n[0], L("ks_gradprod.x", ks_gradprod<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                          (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[0]));
-      launches += 3;
     }
     const double leb = (2.0 * M_PI / n[0]) * (2.0 * M_PI / n[1]) * (2.0 * M_PI / n[2]);
     double s[4];
@@ -513,14 +534,71 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::h2d(Tr, hs_in + nreal, sizeof(T) * nreal, st));
     *ks = solve_state(Tk, Tk, 0);
     // p_T = -(c(T) - d1)
-    simt::launch(k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, Tr, (T)1, (const T*)Tr, (T)-1, (const T*)Tk);
-    launches++;
+    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, Tr, (T)1, (const T*)Tr, (T)-1, (const T*)Tk);
     *ka = solve_adjoint(Tr, Tr, 1, 1);
     GLIA_CHECK(rt::d2h(hs_out, Tk, sizeof(T) * nreal, st));
     GLIA_CHECK(rt::d2h(hs_out + nreal, Tr, sizeof(T) * nreal, st));
     sync();
     std::memcpy(cTh, hs_out, sizeof(T) * nreal);
     std::memcpy(p0h, hs_out + nreal, sizeof(T) * nreal);
+  }
+
+  // ------------------------------------------------- type-erased face ----
+  void* stream_handle() override { return (void*)(intptr_t)st; }
+  void v_fft_r2c(const void* f, void* fhat) override { fft3d_r2c(*this, (const T*)f, (C*)fhat); }
+  void v_fft_c2r(const void* fhat, void* f) override { fft3d_c2r(*this, (const C*)fhat, (T*)f); }
+  void v_gradient(void* gx, void* gy, void* gz, const void* x, int m) override {
+    gradient((T*)gx, (T*)gy, (T*)gz, (const T*)x, m);
+  }
+  void v_divergence(void* div, const void* dx, const void* dy, const void* dz) override {
+    divergence((T*)div, (const T*)dx, (const T*)dy, (const T*)dz);
+  }
+  void v_set_diffusion(const void* k, const double ka[3], double ks) override { set_diffusion((const T*)k, ka, ks); }
+  void v_set_diffusion_tissue(const void* wm, const void* gm, const void* csf, double ks, double kgm, double kglm,
+                              double fsum) override {
+    set_diffusion_tissue((const T*)wm, (const T*)gm, (const T*)csf, ks, kgm, kglm, fsum);
+  }
+  void v_set_secondary_k(const void* kt) override {
+    GLIA_CHECK(rt::copy(ktil, kt, sizeof(T) * nreal, st));
+    sync();
+  }
+  void v_set_reaction(const void* rh) override {
+    GLIA_CHECK(rt::copy(rho, rh, sizeof(T) * nreal, st));
+    sync();
+  }
+  void v_set_reaction_tissue(const void* wm, const void* gm, const void* csf, double rs, double rgm,
+                             double rglm) override {
+    set_reaction_tissue((const T*)wm, (const T*)gm, (const T*)csf, rs, rgm, rglm);
+  }
+  void v_apply_D(void* dc, const void* c, int secondary) override { apply_D((T*)dc, (const T*)c, secondary != 0); }
+  void v_prec_factor() override { prec_factor(); }
+  int v_diffusion_solve(void* c, double dts) override {
+    const int k = diffusion_solve((T*)c, dts);
+    sync();
+    return k;
+  }
+  void v_set_ksp_tolerances(double rt_, double at_, double dt_, int mi) override {
+    rtol = rt_; abstol = at_; dtol = dt_; maxit = mi;
+  }
+  void v_resize_history(int nt_, double dt_) override { resize_history(nt_, dt_); }
+  void* v_history(int which, int i) override { return (void*)hist(which, i); }
+  void v_reaction(void* ct, const void* clin, double dtr) override {
+    reaction((T*)ct, (const T*)clin, (T)dtr, nullptr);
+    sync();
+  }
+  int v_solve_state(const void* c0, void* cT, int lin) override { return solve_state((const T*)c0, (T*)cT, lin); }
+  int v_solve_adjoint(const void* pT, void* p0o, int lin, int store) override {
+    return solve_adjoint((const T*)pT, (T*)p0o, lin, store);
+  }
+  void v_grad_kappa_rho(const void* wm, const void* gm, const void* csf, double out[6]) override {
+    grad_kappa_rho((const T*)wm, (const T*)gm, (const T*)csf, out);
+  }
+  void v_profile_begin() override { sync(); prof.begin(); }
+  std::string v_profile_end() override { return prof.end(st); }
+  void v_timer_start() override { timer.start(st); }
+  double v_timer_stop_ms() override { return timer.stop_ms(st); }
+  void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0o, int* ks, int* ka) override {
+    forward_adjoint_host((const T*)c0, (const T*)d1, (T*)cT, (T*)p0o, ks, ka);
   }
 };
 

@@ -1,0 +1,50 @@
+// engine_base.h -- the precision-erased interface between the C ABI (c_api.cu) and the
+// templated engine (engine.cuh, instantiated in engine_f32.cu / engine_f64.cu).
+#pragma once
+#include <string>
+
+namespace glia {
+
+struct EngineError {
+  std::string msg;
+};
+
+// Type-erased face of Engine<T> used by the C ABI (c_api.cu); `void*` arguments are device
+// pointers to T unless a name ends in _host.
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  long long launches = 0;
+  virtual int precision() const = 0;
+  virtual void* stream_handle() = 0;
+  virtual void v_fft_r2c(const void* f, void* fhat) = 0;
+  virtual void v_fft_c2r(const void* fhat, void* f) = 0;
+  virtual void v_gradient(void* gx, void* gy, void* gz, const void* x, int mask) = 0;
+  virtual void v_divergence(void* div, const void* dx, const void* dy, const void* dz) = 0;
+  virtual void v_set_diffusion(const void* k, const double kavg[3], double k_scale) = 0;
+  virtual void v_set_diffusion_tissue(const void* wm, const void* gm, const void* csf, double ks, double kgm,
+                                      double kglm, double filter_sum) = 0;
+  virtual void v_set_secondary_k(const void* kt) = 0;
+  virtual void v_set_reaction(const void* rho) = 0;
+  virtual void v_set_reaction_tissue(const void* wm, const void* gm, const void* csf, double rs, double rgm,
+                                     double rglm) = 0;
+  virtual void v_apply_D(void* dc, const void* c, int secondary) = 0;
+  virtual void v_prec_factor() = 0;
+  virtual int v_diffusion_solve(void* c, double dt) = 0;
+  virtual void v_set_ksp_tolerances(double rtol, double abstol, double dtol, int maxit) = 0;
+  virtual void v_resize_history(int nt, double dt) = 0;
+  virtual void* v_history(int which, int i) = 0;
+  virtual void v_reaction(void* ct, const void* clin, double dt) = 0;
+  virtual int v_solve_state(const void* c0, void* cT, int linearized) = 0;
+  virtual int v_solve_adjoint(const void* pT, void* p0, int linearized, int adjoint_store) = 0;
+  virtual void v_grad_kappa_rho(const void* wm, const void* gm, const void* csf, double out[6]) = 0;
+  virtual void v_profile_begin() = 0;
+  virtual std::string v_profile_end() = 0;
+  virtual void v_timer_start() = 0;
+  virtual double v_timer_stop_ms() = 0;
+  virtual void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
+};
+EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx);
+EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx);
+
+}  // namespace glia

@@ -1,0 +1,6 @@
+// engine_f32.cu -- single-precision instantiation of the engine and its kernels.
+#include "engine.cuh"
+#include "spectral3d.cuh"
+namespace glia {
+EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx) { return new Engine<float>(n, device, dt_ctx); }
+}  // namespace glia

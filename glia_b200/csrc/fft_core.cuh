@@ -38,7 +38,7 @@ template <> struct FftPlan<32>  { static constexpr int E = 8,  P = 2, R0 = 8,  R
 template <> struct FftPlan<64>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 8,  R2 = 1; };
 template <> struct FftPlan<128> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 8,  R2 = 1; };
 template <> struct FftPlan<256> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 16, R2 = 1; };
-template <> struct FftPlan<512> { static constexpr int E = 8,  P = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+template <> struct FftPlan<512> { static constexpr int E = 16, P = 3, R0 = 8,  R1 = 8,  R2 = 8; };
 
 // cos(2 pi j / 32), j = 0..8 -- enough for every radix <= 32 by symmetry
 __host__ __device__ constexpr double cos32(int j) {

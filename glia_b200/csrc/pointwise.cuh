@@ -44,7 +44,7 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ partial,
 
 // KSPConvergedDefault at iteration 0 with a non-zero initial guess:
 //   rnorm0 = ||M^-1 b|| (or dp if that is 0), ttol = max(rtol*rnorm0, abstol), test dp <= ttol.
-__global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
+static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
                            double rtol, double abstol) {
   double b[2], rz[2];
   sum_partials<2>(pb, nb, b);
@@ -204,7 +204,7 @@ __global__ void k_dot3(long n, const T* __restrict__ t, const T* __restrict__ m0
     partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
   }
 }
-__global__ void k_sum4(const double* partial, int n, double* out) {
+static __global__ void k_sum4(const double* partial, int n, double* out) {
   double o[4];
   sum_partials<4>(partial, n, o);
   if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3]; }

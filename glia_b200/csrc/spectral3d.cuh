@@ -51,19 +51,18 @@ template <typename T>
 void fft3d_r2c(Engine<T>& E, const T* f, cplx<T>* fhat) {
   using C = cplx<T>;
   const TileS ty = E.tile_y(), tx = E.tile_x();
-  GLIA_DISPATCH_N(E.n[2], simt::launch(kz_r2c<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
+  GLIA_DISPATCH_N(E.n[2], E.L("kz_r2c", kz_r2c<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
                                        Engine<T>::template smem_z<N>(), E.st, E.lines_z(), const_cast<T*>(f),
                                        (const T*)nullptr, (const double*)nullptr, E.shat, (const C*)E.tw[2],
                                        (const int*)nullptr));
-  GLIA_DISPATCH_N(E.n[1], simt::launch(ks_c2c<T, N, -1>, Engine<T>::grid_s(ty), Engine<T>::template block_s<N>(),
+  GLIA_DISPATCH_N(E.n[1], E.L("ks_c2c", ks_c2c<T, N, -1>, Engine<T>::grid_s(ty), Engine<T>::template block_s<N>(),
                                        Engine<T>::template smem_s<N>(), E.st, ty, (const C*)E.shat, E.shat,
                                        (const C*)E.tw[1], (const int*)nullptr));
-  GLIA_DISPATCH_N(E.n[0], simt::launch(ks_c2c<T, N, -1>, Engine<T>::grid_s(tx), Engine<T>::template block_s<N>(),
+  GLIA_DISPATCH_N(E.n[0], E.L("ks_c2c", ks_c2c<T, N, -1>, Engine<T>::grid_s(tx), Engine<T>::template block_s<N>(),
                                        Engine<T>::template smem_s<N>(), E.st, tx, (const C*)E.shat, E.shat,
                                        (const C*)E.tw[0], (const int*)nullptr));
-  simt::launch(k_unpack_half<T>, Engine<T>::grid_pw(E.ncplx), dim3(256), 0, E.st, E.n[0], E.n[1], E.n2c,
+  E.L("k_unpack_half", k_unpack_half<T>, Engine<T>::grid_pw(E.ncplx), dim3(256), 0, E.st, E.n[0], E.n[1], E.n2c,
                (const C*)E.shat, fhat);
-  E.launches += 4;
   E.sync();
 }
 
@@ -71,17 +70,16 @@ template <typename T>
 void fft3d_c2r(Engine<T>& E, const cplx<T>* fhat, T* f) {
   using C = cplx<T>;
   const TileS ty = E.tile_y(), tx = E.tile_x();
-  simt::launch(k_pack_half<T>, Engine<T>::grid_pw(E.ncplx), dim3(256), 0, E.st, E.n[0], E.n[1], E.n2c, fhat, E.shat);
-  GLIA_DISPATCH_N(E.n[0], simt::launch(ks_c2c<T, N, +1>, Engine<T>::grid_s(tx), Engine<T>::template block_s<N>(),
+  E.L("k_pack_half", k_pack_half<T>, Engine<T>::grid_pw(E.ncplx), dim3(256), 0, E.st, E.n[0], E.n[1], E.n2c, fhat, E.shat);
+  GLIA_DISPATCH_N(E.n[0], E.L("ks_c2c", ks_c2c<T, N, +1>, Engine<T>::grid_s(tx), Engine<T>::template block_s<N>(),
                                        Engine<T>::template smem_s<N>(), E.st, tx, (const C*)E.shat, E.shat,
                                        (const C*)E.tw[0], (const int*)nullptr));
-  GLIA_DISPATCH_N(E.n[1], simt::launch(ks_c2c<T, N, +1>, Engine<T>::grid_s(ty), Engine<T>::template block_s<N>(),
+  GLIA_DISPATCH_N(E.n[1], E.L("ks_c2c", ks_c2c<T, N, +1>, Engine<T>::grid_s(ty), Engine<T>::template block_s<N>(),
                                        Engine<T>::template smem_s<N>(), E.st, ty, (const C*)E.shat, E.shat,
                                        (const C*)E.tw[1], (const int*)nullptr));
-  GLIA_DISPATCH_N(E.n[2], simt::launch(kz_c2r<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
+  GLIA_DISPATCH_N(E.n[2], E.L("kz_c2r", kz_c2r<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
                                        Engine<T>::template smem_z<N>(), E.st, E.lines_z(), (const C*)E.shat, f,
                                        (const T*)nullptr, (double*)nullptr, (const C*)E.tw[2], (const int*)nullptr));
-  E.launches += 4;
   E.sync();
 }
 

@@ -151,6 +151,20 @@ class RDHandle:
         self._ck(self.lib.glia_rd_grad_kappa_rho(self._h, _ptr(wm), _ptr(gm), _ptr(csf), out))
         return np.array(list(out))
 
+    # -- per-kernel profile -----------------------------------------------------------
+    def profile_begin(self):
+        self._ck(self.lib.glia_rd_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> {tag: (launches, total_ms)}"""
+        buf = C.create_string_buffer(16384)
+        self._ck(self.lib.glia_rd_profile_end(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, cnt, ms = line.split()
+            out[tag] = (int(cnt), float(ms))
+        return out
+
     # -- timing / host entry ---------------------------------------------------------
     def timer_start(self):
         self._ck(self.lib.glia_rd_timer_start(self._h))

@@ -116,6 +116,13 @@ int glia_rd_solve_adjoint(glia_rd_t* h, const void* pT, void* p0, int linearized
  * evaluateHessian (DerivativeOperatorsRD.cpp:270-320, 355-407). */
 int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double out[6]);
 
+/* ---- per-kernel profile (CUDA events around every launch on the handle's stream) ---- */
+/* begin: start recording; end: stop, and write one "tag launches total_ms" line per kernel
+ * family into buf (NUL-terminated, truncated to buflen).  Replaces the reference's
+ * EventRegistry timers (3rdparty/timings/EventTimings.hpp:140-176) for this path. */
+int glia_rd_profile_begin(glia_rd_t* h);
+int glia_rd_profile_end(glia_rd_t* h, char* buf, int buflen);
+
 /* ---- timing helper (CUDA events on the handle's stream) --------------------------- */
 int glia_rd_timer_start(glia_rd_t* h);
 int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms);

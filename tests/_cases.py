@@ -1,0 +1,239 @@
+"""Parity cases shared by the emulator (CPU) and the CUDA (gpu) test modules.
+
+A `Backend` hides where fields live: NumPy arrays handed to the emulator build by host
+pointer, or torch CUDA tensors handed to libglia_rd.so by device pointer.  Every case runs the
+same inputs through the C ABI and through the CPU oracle and returns the comparison.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from glia_b200.rd import RDHandle
+from oracle import rd_oracle as O
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-10}  # BASELINE.json north_star
+
+
+def rel(a, b):
+    wide = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = np.asarray(a, dtype=wide).ravel()
+    b = np.asarray(b, dtype=wide).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+class NumpyBackend:
+    """emulator: 'device' memory is host memory."""
+    def __init__(self, lib_path):
+        self.lib_path = lib_path
+
+    def handle(self, n, dtype, dt_ctx=0.5):
+        return RDHandle(n, "f32" if np.dtype(dtype) == np.float32 else "f64", dt_ctx=dt_ctx,
+                        lib_path=self.lib_path)
+
+    def put(self, a):
+        return np.ascontiguousarray(a).copy()
+
+    def empty(self, shape, dtype):
+        return np.zeros(shape, dtype)
+
+    def get(self, a):
+        return np.array(a)
+
+
+class TorchBackend:
+    def __init__(self, lib_path, device=0):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        self.device = device
+        self.lib_path = lib_path
+
+    def handle(self, n, dtype, dt_ctx=0.5):
+        return RDHandle(n, "f32" if np.dtype(dtype) == np.float32 else "f64", device=self.device,
+                        dt_ctx=dt_ctx, lib_path=self.lib_path)
+
+    def put(self, a):
+        t = self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        self.torch.cuda.synchronize()
+        return t
+
+    def empty(self, shape, dtype):
+        td = {np.dtype(np.float32): self.torch.float32, np.dtype(np.float64): self.torch.float64,
+              np.dtype(np.complex64): self.torch.complex64, np.dtype(np.complex128): self.torch.complex128}
+        t = self.torch.zeros(tuple(shape), dtype=td[np.dtype(dtype)], device=self.dev)
+        self.torch.cuda.synchronize()
+        return t
+
+    def get(self, a):
+        self.torch.cuda.synchronize()
+        return a.cpu().numpy()
+
+
+def shape3(n):
+    return (n, n, n) if np.isscalar(n) else tuple(n)
+
+
+def smooth_field(shape, dtype, seed, lo=0.0, hi=1.0, kmax=3):
+    """A smooth random periodic field in [lo, hi]."""
+    rng = np.random.default_rng(seed)
+    ax = [2 * np.pi * np.arange(m) / m for m in shape]
+    f = np.zeros(shape)
+    for _ in range(6):
+        kx, ky, kz = rng.integers(0, kmax + 1, 3)
+        ph = rng.uniform(0, 2 * np.pi, 3)
+        f += rng.standard_normal() * (np.cos(kx * ax[0] + ph[0])[:, None, None]
+                                      * np.cos(ky * ax[1] + ph[1])[None, :, None]
+                                      * np.cos(kz * ax[2] + ph[2])[None, None, :])
+    f = (f - f.min()) / (f.max() - f.min())
+    return (lo + (hi - lo) * f).astype(dtype)
+
+
+# ------------------------------------------------------------------ L0 ----
+def case_fft(B, n, dtype, seed=0):
+    sh = shape3(n)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(sh).astype(dtype)
+    cdt = np.complex64 if np.dtype(dtype) == np.float32 else np.complex128
+    h = B.handle(n, dtype)
+    xd = B.put(x)
+    fh = B.empty((sh[0], sh[1], sh[2] // 2 + 1), cdt)
+    h.fft_r2c(xd, fh)
+    ref = O.fft_r2c(x.astype(np.float64))
+    e_fwd = rel(B.get(fh), ref)
+    y = B.empty(sh, dtype)
+    h.fft_c2r(fh, y)
+    e_rt = rel(B.get(y), x.astype(np.float64) * np.prod(sh))
+    # c2r of an oracle spectrum (independent of our own r2c)
+    fo = B.put(ref.astype(cdt))
+    h.fft_c2r(fo, y)
+    e_inv = rel(B.get(y), x.astype(np.float64) * np.prod(sh))
+    h.close()
+    return e_fwd, e_rt, e_inv
+
+
+def case_grad_div(B, n, dtype, seed=1):
+    sh = shape3(n)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(sh).astype(dtype)
+    h = B.handle(n, dtype)
+    xd = B.put(x)
+    g = [B.empty(sh, dtype) for _ in range(3)]
+    h.gradient(g[0], g[1], g[2], xd, 7)
+    ref = O.gradient(x)
+    errs = [rel(B.get(g[i]), ref[i]) for i in range(3)]
+    # masked call leaves unrequested outputs untouched
+    gy2 = B.empty(sh, dtype)
+    h.gradient(None, gy2, None, xd, 2)
+    errs.append(rel(B.get(gy2), ref[1]))
+    d = B.empty(sh, dtype)
+    vx, vy, vz = [rng.standard_normal(sh).astype(dtype) for _ in range(3)]
+    h.divergence(d, B.put(vx), B.put(vy), B.put(vz))
+    errs.append(rel(B.get(d), O.divergence(vx, vy, vz)))
+    h.close()
+    return errs
+
+
+# ------------------------------------------------------------------ L1 ----
+def tissue(shape, dtype):
+    wm = smooth_field(shape, dtype, 11, 0.0, 0.7)
+    gm = smooth_field(shape, dtype, 12, 0.0, 0.3)
+    csf = (np.float64(1.0) - wm - gm).clip(0, 1).astype(dtype) * np.asarray(0.5, dtype)
+    filt = ((wm > 0.1) | (gm > 0.1)).astype(dtype)
+    return wm, gm, csf, filt
+
+
+def case_apply_D(B, n, dtype, sinusoidal=True):
+    sh = shape3(n)
+    k = O.DiffCoef(sh, dtype)
+    h = B.handle(n, dtype)
+    if sinusoidal:
+        k.set_values_sinusoidal(1e-2)
+        h.set_diffusion(B.put(k.kxx), [float(k.kxx_avg)] * 3, 1e-2)
+    else:
+        wm, gm, csf, filt = tissue(sh, dtype)
+        k.set_values(0.05, 0.2, 0.1, wm, gm, csf, filt)
+        h.set_diffusion_tissue(B.put(wm), B.put(gm), B.put(csf), 0.05, 0.2, 0.1, float(filt.sum(dtype=np.float64)))
+    c = smooth_field(sh, dtype, 5) if not sinusoidal else O.test_gaussian(sh[0], dtype)
+    if c.shape != sh:
+        c = smooth_field(sh, dtype, 5)
+    ref = k.apply_D(c)
+    cd = B.put(c)
+    dc = B.empty(sh, dtype)
+    h.apply_D(dc, cd)
+    e1 = rel(B.get(dc), ref)
+    h.apply_D(cd, cd)  # aliasing allowed (PdeOperators.cpp:210)
+    e2 = rel(B.get(cd), ref)
+    h.close()
+    return e1, e2
+
+
+# ------------------------------------------------------------------ L2 ----
+def case_K1(B, dtype, n=64, nsolves=10):
+    """src/test/pdesolver.cpp:7-56 through the C ABI."""
+    k = O.DiffCoef((n, n, n), dtype)
+    k.set_values_sinusoidal(1e-2)
+    ds = O.DiffusionSolver(k, 0.5)
+    h = B.handle(n, dtype, dt_ctx=0.5)
+    h.set_diffusion(B.put(k.kxx), [float(k.kxx_avg)] * 3, 1e-2)
+    h.prec_factor()
+    c = O.test_gaussian(n, dtype)
+    cd = B.put(c)
+    its_g, its_o = [], []
+    for _ in range(nsolves):
+        its_g.append(h.diffusion_solve(cd, 0.02))
+        c = ds.solve(c, 0.02)
+        its_o.append(ds.ksp_itr)
+    out = B.get(cd)
+    h.close()
+    return float(np.sqrt(np.sum(out.astype(np.float64) ** 2))), its_g, its_o, rel(out, c)
+
+
+def make_problem(n, dtype, rho_scale=8.0, k_scale=0.01, seed=3):
+    sh = shape3(n)
+    wm, gm, csf, filt = tissue(sh, dtype)
+    k = O.DiffCoef(sh, dtype)
+    k.set_values(k_scale, 0.2, 0.0, wm, gm, csf, filt)
+    rho = O.reac_coef(rho_scale, 0.2, 0.0, wm, gm, csf)
+    # Gaussian initial condition
+    ax = [2 * np.pi * np.arange(m) / m for m in sh]
+    r2 = ((ax[0] - 3.0)[:, None, None] ** 2 + (ax[1] - 3.3)[None, :, None] ** 2 + (ax[2] - 2.8)[None, None, :] ** 2)
+    c0 = (0.8 * np.exp(-r2 / (2 * 0.35 ** 2))).astype(dtype)
+    return dict(wm=wm, gm=gm, csf=csf, filt=filt, k=k, rho=rho, c0=c0, k_scale=k_scale, rho_scale=rho_scale)
+
+
+def setup_handle(B, P, n, dtype, nt, dt):
+    h = B.handle(n, dtype, dt_ctx=dt)
+    dev = {key: B.put(P[key]) for key in ("wm", "gm", "csf")}
+    h.set_diffusion_tissue(dev["wm"], dev["gm"], dev["csf"], P["k_scale"], 0.2, 0.0,
+                           float(P["filt"].sum(dtype=np.float64)))
+    h.set_reaction_tissue(dev["wm"], dev["gm"], dev["csf"], P["rho_scale"], 0.2, 0.0)
+    h.prec_factor()
+    h.resize_history(nt, dt)
+    return h, dev
+
+
+def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_grad=True):
+    """solveState(0) -> p_T = -(c(T) - d) -> solveAdjoint(1) -> kappa/rho gradient integrals."""
+    sh = shape3(n)
+    P = make_problem(n, dtype)
+    pde = O.PdeOperatorsRD(P["k"], P["rho"], nt, dt, dt_ctx=dt, adjoint_store=adjoint_store)
+    cT_ref = pde.solve_state(P["c0"], 0)
+    d1 = (0.9 * cT_ref + 0.05 * P["c0"]).astype(dtype)
+    pT = (-(cT_ref - d1)).astype(dtype)
+    p0_ref = pde.solve_adjoint(pT, 1)
+
+    h, dev = setup_handle(B, P, n, dtype, nt, dt)
+    cT = B.empty(sh, dtype)
+    its_s = h.solve_state(B.put(P["c0"]), cT, 0)
+    res = {"its_state": (its_s, pde.ksp_state), "cT": rel(B.get(cT), cT_ref)}
+    p0 = B.empty(sh, dtype)
+    its_a = h.solve_adjoint(B.put(pT), p0, 1, adjoint_store)
+    res["its_adj"] = (its_a, pde.ksp_adj)
+    res["p0"] = rel(B.get(p0), p0_ref)
+    if with_grad:
+        g = h.grad_kappa_rho(dev["wm"], dev["gm"], dev["csf"])
+        g_ref = O.grad_kappa_rho(pde, P["wm"], P["gm"], P["csf"])
+        res["grad"] = float(np.max(np.abs(g - g_ref) / np.maximum(np.abs(g_ref), 1e-300)))
+        res["grad_vals"] = (g, g_ref)
+    h.close()
+    return res

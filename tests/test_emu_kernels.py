@@ -1,0 +1,52 @@
+"""CPU tests of the product kernel sources and host drivers through the test-only SIMT
+emulator build (tests/emu): same C ABI, same code, OS threads instead of CUDA threads.
+Small grids only; the parity tests proper are the gpu ones."""
+import numpy as np
+import pytest
+
+import _cases as Cs
+
+DT = [np.float32, np.float64]
+EPS = {np.dtype(np.float32): 2e-6, np.dtype(np.float64): 1e-13}
+
+
+@pytest.fixture(scope="module")
+def B(emu_lib):
+    return Cs.NumpyBackend(emu_lib)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [32, (32, 64, 32)])
+def test_fft(B, n, dtype):
+    for e in Cs.case_fft(B, n, dtype):
+        assert e < EPS[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_grad_div(B, dtype):
+    for e in Cs.case_grad_div(B, (32, 32, 64), dtype):
+        assert e < EPS[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("sinusoidal", [True, False])
+def test_apply_D(B, dtype, sinusoidal):
+    for e in Cs.case_apply_D(B, 32, dtype, sinusoidal):
+        assert e < 10 * EPS[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_pcg_matches_oracle_iterations(B, dtype):
+    nrm, its_g, its_o, err = Cs.case_K1(B, dtype, n=32, nsolves=2)
+    assert its_g == its_o
+    assert err < Cs.TOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_forward_adjoint_gradient(B, dtype):
+    r = Cs.case_forward_adjoint(B, 32, dtype, nt=2, dt=0.05)
+    assert r["its_state"][0] == r["its_state"][1]
+    assert r["its_adj"][0] == r["its_adj"][1]
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["cT"] < tol and r["p0"] < tol
+    assert r["grad"] < 10 * tol, r["grad_vals"]

@@ -1,0 +1,188 @@
+"""Parity of the CUDA path (libglia_rd.so through the C ABI, torch CUDA tensors as device
+memory) against the CPU oracle on the same seeded inputs, plus size-independent properties
+at the BASELINE.json sizes.  Tolerances are north_star's: relative L2 1e-5 (f32), 1e-10 (f64)."""
+import numpy as np
+import pytest
+
+import _cases as Cs
+from oracle import rd_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = [np.float32, np.float64]
+EPS = {np.dtype(np.float32): 2e-6, np.dtype(np.float64): 1e-13}
+
+
+@pytest.fixture(scope="module")
+def B(cuda_lib, torch_cuda):
+    return Cs.TorchBackend(cuda_lib)
+
+
+def test_library_is_the_cuda_build(B):
+    h = B.handle(32, np.float32)
+    assert h.lib.glia_rd_build_info() == b"cuda-sm_100a"
+    h.close()
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [32, 64, 128, 256, (64, 32, 128)])
+def test_fft(B, n, dtype):
+    for e in Cs.case_fft(B, n, dtype):
+        assert e < EPS[np.dtype(dtype)]
+
+
+def test_fft_512_f32(B):
+    for e in Cs.case_fft(B, 512, np.float32):
+        assert e < 3e-6
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [64, 256, (128, 64, 32)])
+def test_grad_div(B, n, dtype):
+    for e in Cs.case_grad_div(B, n, dtype):
+        assert e < EPS[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n,sinusoidal", [(64, True), (64, False), (128, False), (256, False)])
+def test_apply_D(B, n, dtype, sinusoidal):
+    for e in Cs.case_apply_D(B, n, dtype, sinusoidal):
+        assert e < 10 * EPS[np.dtype(dtype)]
+
+
+def test_apply_D_512_f32(B):
+    for e in Cs.case_apply_D(B, 512, np.float32, False):
+        assert e < 3e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_K1_reference_unit_test(B, dtype):
+    """src/test/pdesolver.cpp:7-56 -- ||c||_2 == Approx(2.0487), ksp_itr_ == 5."""
+    nrm, its_g, its_o, err = Cs.case_K1(B, dtype)
+    assert abs(nrm - 2.0487) < 100 * np.finfo(np.float32).eps * (1 + 2.0487) + 5e-5
+    assert its_g[-1] == 5
+    assert its_g == its_o
+    assert err < Cs.TOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n,nt", [(64, 6), (128, 2)])
+def test_forward_adjoint_gradient(B, n, nt, dtype):
+    r = Cs.case_forward_adjoint(B, n, dtype, nt=nt, dt=0.04)
+    assert r["its_state"][0] == r["its_state"][1]
+    assert r["its_adj"][0] == r["its_adj"][1]
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["cT"] < tol and r["p0"] < tol
+    assert r["grad"] < 10 * tol, r["grad_vals"]
+
+
+def test_adjoint_without_store(B):
+    r = Cs.case_forward_adjoint(B, 64, np.float64, nt=2, dt=0.04, adjoint_store=False, with_grad=False)
+    assert r["its_adj"][0] == r["its_adj"][1]
+    assert r["p0"] < 1e-10
+
+
+# ---- size-independent properties at the headline size -------------------------------------
+@pytest.mark.parametrize("n", [256])
+def test_properties_at_full_size(B, n):
+    torch = B.torch
+    dtype = np.float32
+    sh = (n, n, n)
+    P = Cs.make_problem(n, dtype)
+    h, dev = Cs.setup_handle(B, P, n, dtype, nt=2, dt=0.04)
+    g = torch.Generator(device=B.dev).manual_seed(0)
+    u = torch.randn(sh, device=B.dev, dtype=torch.float32, generator=g)
+    v = torch.randn(sh, device=B.dev, dtype=torch.float32, generator=g)
+    torch.cuda.synchronize()
+    Du, Dv, Duv = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+    h.apply_D(Du, u)
+    h.apply_D(Dv, v)
+    # linearity
+    w = (2.0 * u - 3.0 * v).contiguous()
+    torch.cuda.synchronize()
+    h.apply_D(Duv, w)
+    lin = (Duv - (2.0 * Du - 3.0 * Dv)).double().norm() / Duv.double().norm()
+    assert float(lin) < 1e-5
+    # self-adjointness <u, D v> == <D u, v>, and D annihilates constants, and sum(D u) == 0
+    a = float((u.double() * Dv.double()).sum())
+    b = float((Du.double() * v.double()).sum())
+    assert abs(a - b) < 1e-5 * max(abs(a), abs(b))
+    ones = torch.ones_like(u)
+    torch.cuda.synchronize()
+    h.apply_D(Duv, ones)
+    assert float(Duv.abs().max()) < 1e-6
+    assert abs(float(Du.double().sum())) < 1e-4 * float(Du.double().abs().sum())
+    # Crank-Nicolson solve: residual of (I - dt/4 D) x = (I + dt/4 D) c, checked with apply_D
+    c = dev["wm"].clone()
+    x = c.clone()
+    torch.cuda.synchronize()
+    its = h.diffusion_solve(x, 0.02)
+    Dc, Dx = torch.empty_like(c), torch.empty_like(c)
+    h.apply_D(Dc, c)
+    h.apply_D(Dx, x)
+    res = (x - 0.01 * Dx) - (c + 0.01 * Dc)
+    assert 0 < its < 20
+    assert float(res.double().norm() / c.double().norm()) < 1e-5
+    # mass conservation of the diffusion step (D has zero mean)
+    assert abs(float(x.double().sum() - c.double().sum())) < 1e-6 * float(c.double().sum())
+    # FFT round trip
+    fh = torch.empty((n, n, n // 2 + 1), dtype=torch.complex64, device=B.dev)
+    y = torch.empty_like(u)
+    torch.cuda.synchronize()
+    h.fft_r2c(u, fh)
+    h.fft_c2r(fh, y)
+    assert float((y / n ** 3 - u).double().norm() / u.double().norm()) < 2e-6
+    # Parseval with the half spectrum
+    e_real = float((u.double() ** 2).sum())
+    wgt = torch.full((n // 2 + 1,), 2.0, device=B.dev, dtype=torch.float64)
+    wgt[0] = 1.0
+    wgt[-1] = 1.0
+    e_spec = float(((fh.real.double() ** 2 + fh.imag.double() ** 2) * wgt).sum()) / n ** 3
+    assert abs(e_real - e_spec) < 1e-5 * e_real
+    h.close()
+
+
+def test_forward_is_deterministic_and_bounded(B):
+    """Same inputs twice -> bitwise identical c(T) (fixed-order reductions); logistic growth
+    keeps c within [min - eps, 1]."""
+    n, nt, dt = 128, 3, 0.04
+    P = Cs.make_problem(n, np.float32)
+    h, dev = Cs.setup_handle(B, P, n, np.float32, nt, dt)
+    c0 = B.put(P["c0"])
+    a, b = B.empty((n, n, n), np.float32), B.empty((n, n, n), np.float32)
+    i1 = h.solve_state(c0, a, 0)
+    i2 = h.solve_state(c0, b, 0)
+    assert i1 == i2
+    assert B.torch.equal(a, b)
+    assert float(a.max()) <= 1.0 + 1e-6
+    h.close()
+
+
+def test_reaction_kernels(B):
+    n = 64
+    for dtype in DT:
+        P = Cs.make_problem(n, dtype)
+        h, dev = Cs.setup_handle(B, P, n, dtype, 1, 0.04)
+        c = Cs.smooth_field((n, n, n), dtype, 9, 0.0, 0.999)
+        c[0, 0, 0] = 1.0  # a = c/(1-c) = inf branch
+        cd = B.put(c)
+        h.reaction(cd, None, 0.04)
+        ref = O.reaction_nonlinear(c, P["rho"], 0.04)
+        assert Cs.rel(B.get(cd), ref) < 5 * EPS[np.dtype(dtype)]
+        u = Cs.smooth_field((n, n, n), dtype, 10, -1.0, 1.0)
+        ud = B.put(u)
+        h.reaction(ud, B.put(c), 0.04)
+        assert Cs.rel(B.get(ud), O.reaction_linearized(u, c, P["rho"], 0.04)) < 5 * EPS[np.dtype(dtype)]
+        h.close()
+
+
+def test_error_paths(B):
+    from glia_b200 import GliaRdError
+    with pytest.raises(GliaRdError, match="powers of two"):
+        B.handle(48, np.float32)
+    h = B.handle(32, np.float32)
+    with pytest.raises(GliaRdError, match="resize_history"):
+        h.solve_state(B.empty((32, 32, 32), np.float32), None, 0)
+    h.resize_history(2, 0.1)
+    with pytest.raises(GliaRdError, match="out of range"):
+        h.history_ptr(0, 7)
+    h.close()
