@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- RD forward+adjoint time-steps/sec (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One bench "step" = one forward (solveState) + adjoint (solveAdjoint) solve of `nt` Strang time
+steps over one synthetic atlas-shaped input (config[1] of BASELINE.json: 256^3, single
+precision, kappa = 0.01, rho = 8, nt = 25, dt = 0.04, time histories stored).  The reported
+`value` is nt * K / T time-steps per second, T timed with CUDA events on the library's stream
+between barriers, max over ranks.
+
+  value     inputs resident in HBM when the timed region starts (glia_rd_forward_adjoint)
+  e2e       the same through the host-buffer C-ABI call (glia_rd_forward_adjoint_host):
+            H2D of c0 and d1 and D2H of c(T) and p(0) inside the timed region
+  roofline  dominant kernel: algorithmic bytes per launch / average launch duration (CUDA
+            events around every launch of one extra, untimed-for-`value` step) vs the measured
+            HBM peak of MEASURED_PEAKS.json; `kernels` lists every kernel family the same way
+  cpu_baseline / --impl reference
+            the CPU restatement of the reference path (oracle/rd_oracle_torch.py: reference
+            operation order, all host threads) on a bounded sample of the same workload
+
+N > 1 (torchrun, one rank per GPU): independent replicas of the same solve, no data-path
+collective ("scaling": "weak"); the slab-decomposed single solve is described in DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "rd_forward_adjoint_time_steps_per_sec"
+UNIT = "time-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--nt", type=int, default=25)
+    ap.add_argument("--dt", type=float, default=0.04)
+    ap.add_argument("--rho", type=float, default=8.0)
+    ap.add_argument("--kappa", type=float, default=0.01)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"{a.n}^3 RD forward+adjoint (solveState + solveAdjoint), synthetic WM/GM/CSF atlas, "
+                    f"{'single' if a.precision == 'f32' else 'double'} precision",
+        "n": a.n, "nt": a.nt, "dt": a.dt, "rho": a.rho, "kappa": a.kappa, "r_gm": 0.0, "k_gm": 0.0,
+        "time_steps_per_bench_step": a.nt,
+        "histories": "c_, c_half_, p_ stored (adjoint_store=1)",
+        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+        "l2": "working set (time histories, >= 5 GB at 256^3) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+def make_inputs(a):
+    from glia_b200 import synthetic as S
+    dtype = np.float32 if a.precision == "f32" else np.float64
+    atlas = S.make_atlas(a.n, seed=0, dtype=dtype)
+    c0 = S.make_initial_condition(atlas, seed=0, dtype=dtype)
+    return atlas, c0, dtype
+
+
+# ------------------------------------------------------------------ clocks ----
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------- algorithmic bytes ----
+# Sweep model of SURVEY.md 8(d) / DESIGN.md: bytes per launch in units of F = one real field.
+ALG_F = {
+    "kz_deriv2": 3, "ks_deriv2.y": 4, "ks_deriv2.x.matvec": 4, "ks_deriv2.x.rhs": 5, "ks_deriv2.x": 4,
+    "kz_r2c": 2, "kz_r2c.axpy": 4, "ks_c2c.y": 2, "ks_pc": 2, "kz_c2r.rz": 3, "kz_c2r": 2, "kz_c2r.norm": 1,
+    "k_cg_update": 5, "k_reaction": 4, "k_reaction_lin": 4, "k_axpby": 3,
+    "k_pcg_alpha": 0, "k_pcg_beta": 0, "k_pcg_init": 0,
+}
+
+
+def step_bytes_model(F, its_per_solve_total, nsolves, nt):
+    """A_min of SURVEY.md 8(d): F * [ sum_solves (33 + 30 m_i) + 10 per time step ]."""
+    return F * (33.0 * nsolves + 30.0 * its_per_solve_total + 10.0 * nt)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(tag):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(tag)
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------- CPU arm ----
+def cpu_reference_sample(a, atlas, c0, nt_sample):
+    """Build the callable that runs ONE bounded sample (nt_sample forward+adjoint time steps at the
+    bench grid) of the restated reference CPU path; returns (fn, cores, description)."""
+    import torch
+    from oracle import rd_oracle_torch as OT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tdt = torch.float32 if a.precision == "f32" else torch.float64
+    wm = torch.from_numpy(atlas["wm"]).to(tdt)
+    k = (a.kappa * wm).contiguous()
+    rho = (a.rho * wm).contiguous()
+    kavg = float(k.double().sum() / float(atlas["filter"].astype(np.float64).sum()))
+    c0t = torch.from_numpy(c0).to(tdt)
+    d1 = (0.9 * c0t).contiguous()
+
+    def run():
+        cT, p0, pde = OT.forward_adjoint(k, kavg, a.kappa, rho, c0t, d1, nt_sample, a.dt)
+        return pde.ksp_state + pde.ksp_adj
+
+    desc = (f"{nt_sample} forward+adjoint time step(s) at {a.n}^3 {a.precision}, restated reference CPU path "
+            f"(3-D FFT grad/div, 12 FFTs per PCG iteration, torch CPU FFT + elementwise, {cores} threads); "
+            f"no MPI/PETSc/AccFFT on this box")
+    return run, cores, desc
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    atlas, c0, _ = make_inputs(a)
+    run, cores, desc = cpu_reference_sample(a, atlas, c0, a.ref_nt)
+    t_start = time.perf_counter()
+    done_w = 0
+    for _ in range(a.warmup):
+        run()
+        done_w += 1
+        if time.perf_counter() - t_start > a.ref_budget_s / 3:
+            break
+    times = []
+    its = 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        t1 = time.perf_counter()
+        its = run()
+        times.append(time.perf_counter() - t1)
+        if time.perf_counter() - t_start > a.ref_budget_s:
+            break
+    T = time.perf_counter() - t0
+    k_done = len(times)
+    value = a.ref_nt * k_done / T
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k_done,
+        "warmup": done_w, "ms_per_step": 1e3 * T / k_done, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+        "config": dict(workload_config(a, 1), time_steps_per_bench_step=a.ref_nt,
+                       note="reference arm: each step is a bounded sample of the workload"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "pcg_iterations_per_sample": its},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- GPU arm ----
+def run_b200(a):
+    import torch
+    from glia_b200.rd import RDHandle
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    atlas, c0, dtype = make_inputs(a)
+    F = float(np.dtype(dtype).itemsize) * a.n ** 3
+    h = RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt)
+    put = lambda x: torch.from_numpy(x).to(dev)
+    wm, gm, csf = put(atlas["wm"]), put(atlas["gm"]), put(atlas["csf"])
+    fsum = float(atlas["filter"].astype(np.float64).sum())
+    c0d = put(c0)
+    cT, p0, d1 = torch.empty_like(c0d), torch.empty_like(c0d), torch.empty_like(c0d)
+    torch.cuda.synchronize()
+    h.resize_history(a.nt, a.dt)
+    # data d1: forward solve with (rho, kappa) = (10, 0.025)   -- set-up, untimed
+    h.set_diffusion_tissue(wm, gm, csf, 0.025, 0.0, 0.0, fsum)
+    h.set_reaction_tissue(wm, gm, csf, 10.0, 0.0, 0.0)
+    h.prec_factor()
+    h.solve_state(c0d, d1, 0)
+    # the benchmarked coefficients
+    h.set_diffusion_tissue(wm, gm, csf, a.kappa, 0.0, 0.0, fsum)
+    h.set_reaction_tissue(wm, gm, csf, a.rho, 0.0, 0.0)
+    h.prec_factor()
+
+    # ---- device-resident timed region -------------------------------------------------------
+    for _ in range(a.warmup):
+        ks, ka = h.forward_adjoint(c0d, d1, cT, p0)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = h.launch_count
+    h.timer_start()
+    for _ in range(a.steps):
+        ks, ka = h.forward_adjoint(c0d, d1, cT, p0)
+    ms = h.timer_stop_ms()
+    barrier()
+    launches = h.launch_count - l0
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    value = world * a.nt * a.steps / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer call ----------------------------------------------
+    tdt = torch.float32 if a.precision == "f32" else torch.float64
+    hp = [torch.empty((a.n, a.n, a.n), dtype=tdt).pin_memory() for _ in range(4)]
+    hp[0].copy_(torch.from_numpy(c0))
+    hp[1].copy_(d1.cpu())
+    hn = [t.numpy() for t in hp]
+    h.forward_adjoint_host(hn[0], hn[1], hn[2], hn[3])
+    barrier()
+    h.timer_start()
+    for _ in range(a.steps):
+        h.forward_adjoint_host(hn[0], hn[1], hn[2], hn[3])
+    ms_e2e = h.timer_stop_ms()
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e_value = world * a.nt * a.steps / (ms_e2e * 1e-3)
+    e2e_ok = bool(np.array_equal(hn[2], cT.cpu().numpy()))
+
+    # ---- per-kernel profile of one more step (CUDA events around every launch) ---------------
+    h.profile_begin()
+    h.forward_adjoint(c0d, d1, cT, p0)
+    prof = h.profile_end()
+    peak, peak_src = peaks()
+    kern = {}
+    tot_ms = sum(v[1] for v in prof.values())
+    for tag, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        avg = tms / cnt
+        fb = ALG_F.get(tag)
+        ach = (fb * F / (avg * 1e-3) / 1e9) if fb else None
+        kern[tag] = {"launches": cnt, "avg_us": 1e3 * avg, "share": tms / tot_ms,
+                     "alg_bytes_per_launch": fb * F if fb is not None else None,
+                     "achieved_GBs": ach, "frac": (ach / peak) if ach else None}
+    dom = next(iter(kern))
+    nsolves = 4 * a.nt
+    model_bytes = step_bytes_model(F, ks + ka, nsolves, a.nt)
+    step_ach = model_bytes / (ms * 1e-3 / a.steps) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
+        "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
+        "alg_bytes_per_launch": kern[dom]["alg_bytes_per_launch"], "avg_launch_us": kern[dom]["avg_us"],
+        "share_of_step": kern[dom]["share"],
+        "whole_step": {"alg_bytes": model_bytes, "achieved": step_ach, "frac": step_ach / peak,
+                       "model": "F*[sum_solves(33+30*m_i)+10*nt] (SURVEY 8d A_min)"},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world),
+        "pcg_iterations": {"state": ks, "adjoint": ka, "solves": nsolves, "mean_per_solve": (ks + ka) / nsolves},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * F), "d2h_bytes_per_step": int(2 * F),
+                "ms_per_step": ms_e2e / a.steps, "matches_device_path": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kern,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        run, cores, desc = cpu_reference_sample(a, atlas, c0, a.ref_nt)
+        t0 = time.perf_counter()
+        its = run()
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": a.ref_nt / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": desc, "seconds": tc, "pcg_iterations_per_sample": its}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

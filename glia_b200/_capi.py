@@ -49,6 +49,7 @@ SIGNATURES = {
     "glia_rd_profile_end": (_I, [_P, C.c_char_p, _I]),
     "glia_rd_timer_start": (_I, [_P]),
     "glia_rd_timer_stop_ms": (_I, [_P, C.POINTER(_D)]),
+    "glia_rd_forward_adjoint": (_I, [_P, _P, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
     "glia_rd_forward_adjoint_host": (_I, [_P, _P, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
 }
 

@@ -173,6 +173,14 @@ int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms) {
     if (ms) *ms = t;
   });
 }
+int glia_rd_forward_adjoint(glia_rd_t* h, const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) {
+  return guarded(h, [&](EngineBase& E) {
+    int a = 0, b = 0;
+    E.v_forward_adjoint(c0, d1, cT, p0, &a, &b);
+    if (ks) *ks = a;
+    if (ka) *ka = b;
+  });
+}
 int glia_rd_forward_adjoint_host(glia_rd_t* h, const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) {
   return guarded(h, [&](EngineBase& E) {
     int a = 0, b = 0;

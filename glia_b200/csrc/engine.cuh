@@ -27,6 +27,11 @@ inline int d2h(void* d, const void* s, size_t n, cudaStream_t st) { return (int)
 inline int zero(void* d, size_t n, cudaStream_t st) { return (int)cudaMemsetAsync(d, 0, n, st); }
 inline int sync(cudaStream_t st) { return (int)cudaStreamSynchronize(st); }
 inline int set_device(int d) { return (int)cudaSetDevice(d); }
+inline bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
 inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
@@ -251,7 +256,8 @@ class Engine : public EngineBase {
     GLIA_DISPATCH_N(n[1], L("ks_deriv2.y", ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[1], (T)0, (C*)nullptr,
                                        (C*)nullptr, (double*)nullptr, done));
-    GLIA_DISPATCH_N(n[0], L("ks_deriv2.x", ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+    const char* xtag = EPI == EPI_MATVEC ? "ks_deriv2.x.matvec" : (EPI == EPI_RHS ? "ks_deriv2.x.rhs" : "ks_deriv2.x");
+    GLIA_DISPATCH_N(n[0], L(xtag, ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                        (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[0], alpha, (C*)out1,
                                        (C*)out2, pp, done));
     return (int)grid_s(tx).x;
@@ -262,7 +268,7 @@ class Engine : public EngineBase {
     const TileS ty = tile_y(), tx = tile_x();
     int nblk = 0;
     if (wv) {
-      GLIA_DISPATCH_N(n[2], L("kz_r2c", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], L("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done));
     } else {
       GLIA_DISPATCH_N(n[2], L("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
@@ -277,7 +283,7 @@ class Engine : public EngineBase {
                                        (const C*)shat, shat, (const C*)tw[1], done));
     GLIA_DISPATCH_N(n[2], {
       nblk = (int)grid_z<N>().x;
-      L("kz_c2r", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
+      L(zout ? (want_rz ? "kz_c2r.rz" : "kz_c2r") : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
                    zout, want_rz ? (const T*)rin : (const T*)nullptr, pp, (const C*)tw[2], done);
     });
     return nblk;
@@ -467,7 +473,7 @@ class Engine : public EngineBase {
       if (linearized == 2) solve_incremental(c_t, i, 2, (T)dth);
       if (linearized == 0) GLIA_CHECK(rt::copy(hist(0, i + 1), c_t, sizeof(T) * nreal, st));
     }
-    if (cT) GLIA_CHECK(rt::copy(cT, c_t, sizeof(T) * nreal, st));
+    if (cT && cT != c_t) GLIA_CHECK(rt::copy(cT, c_t, sizeof(T) * nreal, st));
     sync();
     return total;
   }
@@ -490,7 +496,7 @@ class Engine : public EngineBase {
       total += diffusion_solve(p_0, dth);
       GLIA_CHECK(rt::copy(hist(1, it), p_0, sizeof(T) * nreal, st));
     }
-    if (p0out) GLIA_CHECK(rt::copy(p0out, p_0, sizeof(T) * nreal, st));
+    if (p0out && p0out != p_0) GLIA_CHECK(rt::copy(p0out, p_0, sizeof(T) * nreal, st));
     sync();
     return total;
   }
@@ -521,26 +527,42 @@ class Engine : public EngineBase {
     out[3] = leb * s[0]; out[4] = leb * s[1]; out[5] = leb * s[2];
   }
 
-  // ------------------------------------------------- host-buffer entry ----
+  // ------------------------------------------ forward + adjoint entries ----
+  // solveState(0), p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:156-161), solveAdjoint(1)
+  void forward_adjoint(const T* c0, const T* d1, T* cT, T* p0out, int* ks, int* ka) {
+    *ks = solve_state(c0, cT, 0);
+    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, Tr, (T)1, d1, (T)-1, (const T*)c_t);
+    *ka = solve_adjoint(Tr, p0out, 1, 1);
+  }
+  // same with HOST buffers: H2D of c0 and d1, D2H of c(T) and p(0) inside the call.  Pinned
+  // (page-locked) caller buffers are DMA'd directly; pageable ones go through pinned staging.
   void forward_adjoint_host(const T* c0h, const T* d1h, T* cTh, T* p0h, int* ks, int* ka) {
-    // pinned staging so the copies are true async DMA; device scratch: b (c0), w (d1)
-    if (!hs_in) {
-      GLIA_CHECK(rt::host_malloc((void**)&hs_in, sizeof(T) * nreal * 2));
-      GLIA_CHECK(rt::host_malloc((void**)&hs_out, sizeof(T) * nreal * 2));
+    const size_t bytes = sizeof(T) * nreal;
+    const bool pin_in = rt::is_pinned(c0h) && rt::is_pinned(d1h);
+    const bool pin_out = rt::is_pinned(cTh) && rt::is_pinned(p0h);
+    if ((!pin_in || !pin_out) && !hs_in) {
+      GLIA_CHECK(rt::host_malloc((void**)&hs_in, bytes * 2));
+      GLIA_CHECK(rt::host_malloc((void**)&hs_out, bytes * 2));
     }
-    std::memcpy(hs_in, c0h, sizeof(T) * nreal);
-    std::memcpy(hs_in + nreal, d1h, sizeof(T) * nreal);
-    GLIA_CHECK(rt::h2d(Tk, hs_in, sizeof(T) * nreal, st));
-    GLIA_CHECK(rt::h2d(Tr, hs_in + nreal, sizeof(T) * nreal, st));
-    *ks = solve_state(Tk, Tk, 0);
-    // p_T = -(c(T) - d1)
-    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, Tr, (T)1, (const T*)Tr, (T)-1, (const T*)Tk);
-    *ka = solve_adjoint(Tr, Tr, 1, 1);
-    GLIA_CHECK(rt::d2h(hs_out, Tk, sizeof(T) * nreal, st));
-    GLIA_CHECK(rt::d2h(hs_out + nreal, Tr, sizeof(T) * nreal, st));
+    const T *src0 = c0h, *src1 = d1h;
+    if (!pin_in) {
+      std::memcpy(hs_in, c0h, bytes);
+      std::memcpy(hs_in + nreal, d1h, bytes);
+      src0 = hs_in; src1 = hs_in + nreal;
+    }
+    GLIA_CHECK(rt::h2d(Tk, src0, bytes, st));
+    // d1 must survive the forward solve: it goes to work11, which only solveIncremental and
+    // the store-less adjoint use (neither runs here)
+    GLIA_CHECK(rt::h2d(work11, src1, bytes, st));
+    forward_adjoint(Tk, work11, Tk, p_0, ks, ka);
+    T *dst0 = pin_out ? cTh : hs_out, *dst1 = pin_out ? p0h : hs_out + nreal;
+    GLIA_CHECK(rt::d2h(dst0, Tk, bytes, st));
+    GLIA_CHECK(rt::d2h(dst1, p_0, bytes, st));
     sync();
-    std::memcpy(cTh, hs_out, sizeof(T) * nreal);
-    std::memcpy(p0h, hs_out + nreal, sizeof(T) * nreal);
+    if (!pin_out) {
+      std::memcpy(cTh, hs_out, bytes);
+      std::memcpy(p0h, hs_out + nreal, bytes);
+    }
   }
 
   // ------------------------------------------------- type-erased face ----
@@ -597,6 +619,9 @@ class Engine : public EngineBase {
   std::string v_profile_end() override { return prof.end(st); }
   void v_timer_start() override { timer.start(st); }
   double v_timer_stop_ms() override { return timer.stop_ms(st); }
+  void v_forward_adjoint(const void* c0, const void* d1, void* cT, void* p0o, int* ks, int* ka) override {
+    forward_adjoint((const T*)c0, (const T*)d1, (T*)cT, (T*)p0o, ks, ka);
+  }
   void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0o, int* ks, int* ka) override {
     forward_adjoint_host((const T*)c0, (const T*)d1, (T*)cT, (T*)p0o, ks, ka);
   }

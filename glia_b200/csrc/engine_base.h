@@ -42,6 +42,7 @@ class EngineBase {
   virtual std::string v_profile_end() = 0;
   virtual void v_timer_start() = 0;
   virtual double v_timer_stop_ms() = 0;
+  virtual void v_forward_adjoint(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
   virtual void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
 };
 EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx);

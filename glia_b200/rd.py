@@ -174,6 +174,13 @@ class RDHandle:
         self._ck(self.lib.glia_rd_timer_stop_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def forward_adjoint(self, c0, d1, cT=None, p0=None):
+        """Device-buffer forward + adjoint solve; returns (ksp_its_state, ksp_its_adjoint)."""
+        ks, ka = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.glia_rd_forward_adjoint(self._h, _ptr(c0), _ptr(d1), _ptr(cT), _ptr(p0),
+                                                  C.byref(ks), C.byref(ka)))
+        return ks.value, ka.value
+
     def forward_adjoint_host(self, c0, d1, cT, p0):
         """Host-buffer (NumPy) end-to-end call: H2D, forward, adjoint, D2H inside."""
         for a in (c0, d1, cT, p0):

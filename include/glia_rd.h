@@ -127,9 +127,14 @@ int glia_rd_profile_end(glia_rd_t* h, char* buf, int buflen);
 int glia_rd_timer_start(glia_rd_t* h);
 int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms);
 
-/* ---- host-buffer convenience (plugin-style end-to-end call, H2D/D2H inside) -------- */
-/* One forward + adjoint solve with HOST buffers: c0 (in), d1 (data, in), cT (out),
- * p0 (out); adjoint terminal condition -(c(T) - d1) (O = I).  Used for bench `e2e`. */
+/* ---- one objective-gradient evaluation's PDE work ------------------------------------ */
+/* solveState(0), terminal condition p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:
+ * 155-162), solveAdjoint(1) -- the state/adjoint pair every evaluateObjectiveAndGradient
+ * performs.  DEVICE buffers; cT and p0 may be NULL; histories are left in the handle. */
+int glia_rd_forward_adjoint(glia_rd_t* h, const void* c0, const void* d1, void* cT, void* p0,
+                            int* ksp_state, int* ksp_adj);
+/* The same with HOST buffers (plugin-style end-to-end call): H2D of c0 and d1 and D2H of
+ * c(T) and p(0) happen inside the call; page-locked buffers are DMA'd directly. */
 int glia_rd_forward_adjoint_host(glia_rd_t* h, const void* c0_host, const void* d1_host, void* cT_host,
                                  void* p0_host, int* ksp_state, int* ksp_adj);
 

@@ -132,6 +132,7 @@ inline int d2h(void* d, const void* s, size_t n, cudaStream_t st) { return copy(
 inline int zero(void* d, size_t n, cudaStream_t) { std::memset(d, 0, n); return 0; }
 inline int sync(cudaStream_t) { return 0; }
 inline int set_device(int) { return 0; }
+inline bool is_pinned(const void*) { return true; }
 inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
 inline void stream_destroy(cudaStream_t) {}
 inline const char* err_string(int) { return "emu"; }
