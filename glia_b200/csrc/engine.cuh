@@ -232,6 +232,7 @@ class Engine : public EngineBase {
   TileS tile_x() const { return TileS{(long)n[1] * n2c, (long)n2c, n2c / SL, n[1], 0}; }
   LinesZ lines_z() const { return LinesZ{(long)n[0] * n[1] / 2}; }
   template <int N> static size_t smem_s() { return sizeof(C) * N * SL; }
+  template <int N> static size_t smem_s2() { return 2 * sizeof(C) * N * SL; }  // + the kept x tile
   template <int N> static size_t smem_z() { return sizeof(C) * zlines<N>() * zpad<N>(); }
   template <int N> static dim3 block_s() { return dim3(SL * (N / FftPlan<N>::E)); }
   static dim3 grid_s(const TileS& g) { return dim3(g.nchunk * g.n_outer); }
@@ -254,11 +255,12 @@ class Engine : public EngineBase {
                                        lines_z(), x, kfield, acc, (const C*)tw[2], done));
     const TileS ty = tile_y(), tx = tile_x();
     GLIA_DISPATCH_N(n[1], L("ks_deriv2.y", ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
-                                       (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[1], (T)0, (C*)nullptr,
+                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[1], (T)0, (C*)acc,
                                        (C*)nullptr, (double*)nullptr, done));
     const char* xtag = EPI == EPI_MATVEC ? "ks_deriv2.x.matvec" : (EPI == EPI_RHS ? "ks_deriv2.x.rhs" : "ks_deriv2.x");
-    GLIA_DISPATCH_N(n[0], L(xtag, ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
-                                       (const C*)x, (const C*)kfield, (C*)acc, (const C*)tw[0], alpha, (C*)out1,
+    constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
+    GLIA_DISPATCH_N(n[0], L(xtag, ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, tx,
+                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[0], alpha, (C*)out1,
                                        (C*)out2, pp, done));
     return (int)grid_s(tx).x;
   }

@@ -23,6 +23,12 @@ namespace glia {
 // ------------------------------------------------------------ helpers ----
 static constexpr int SL = 16;  // complex columns (lanes) per S tile
 
+// occupancy hint of the S kernels: two resident CTAs per SM for single-precision tiles of <= 256 threads
+template <typename T, int N>
+__host__ __device__ constexpr int s_min_ctas() {
+  return (SL * (N / FftPlan<N>::E) <= 256 && sizeof(T) == 4) ? 2 : 1;
+}
+
 struct TileS {        // S geometry: tile -> (outer, chunk)
   long row_stride;    // complex units between rows along the sweep axis
   long outer_stride;  // complex units between consecutive outer indices
@@ -88,22 +94,24 @@ __device__ __forceinline__ void deriv_inplace(cplx<T> (&v)[FftPlan<N>::E], const
 enum { EPI_SET = 0, EPI_ADD = 1, EPI_PLAIN = 2, EPI_MATVEC = 3, EPI_RHS = 4, EPI_AXPY = 5 };
 
 // S-geometry second-derivative sweep: s = acc + D(k . D x) along the tile axis.
-//   EPI_SET    acc  = D(k D x)
-//   EPI_ADD    acc  = s
+//   EPI_SET    out1 = D(k D x)
+//   EPI_ADD    out1 = s                                   (the caller passes out1 = acc)
 //   EPI_PLAIN  out1 = s                                   (applyD result)
 //   EPI_MATVEC out1 = x + alpha*s ; partial <x, out1>     (operatorA, alpha = -dt/2)
 //   EPI_RHS    out1 = x + alpha*s ; out2 = out1 - (x - alpha*s)   (rhs and r0 = b - A x0)
 //   EPI_AXPY   out1 += alpha*s                            (solveIncremental)
 template <typename T, int N, int EPI>
-__global__ void __launch_bounds__(SL* (N / FftPlan<N>::E))
-ks_deriv2(TileS geo, const cplx<T>* __restrict__ x, const cplx<T>* __restrict__ kf, cplx<T>* acc,
+__global__ void __launch_bounds__(SL* (N / FftPlan<N>::E), s_min_ctas<T, N>())
+ks_deriv2(TileS geo, const cplx<T>* __restrict__ x, const cplx<T>* __restrict__ kf, const cplx<T>* acc,
           const cplx<T>* __restrict__ twt, T alpha, cplx<T>* out1, cplx<T>* out2, double* partial,
           const int* __restrict__ done) {
   using F = LineFft<T, N>;
   constexpr int E = F::E;
+  constexpr bool KEEP_X = (EPI == EPI_MATVEC || EPI == EPI_RHS);
   if (done && *done) return;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
+  cplx<T>* smx = sm + N * SL;  // x tile kept for the epilogue (KEEP_X only)
   const int l = threadIdx.x & (SL - 1), t = threadIdx.x / SL;
   typename F::Tw tw;
   F::load_twiddles(tw, twt, t);
@@ -115,49 +123,62 @@ ks_deriv2(TileS geo, const cplx<T>* __restrict__ x, const cplx<T>* __restrict__ 
 
   cplx<T> v[E], kk[E];
   GLIA_UNROLL
-  for (int g = 0; g < F::Gp(0); ++g)
+  for (int e = 0; e < E; ++e) {
+    const long off = base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride;
+    v[e] = x[off];
+    kk[e] = kf[off];
+  }
+  if (KEEP_X) {
     GLIA_UNROLL
-    for (int a = 0; a < F::R(0); ++a) {
-      const long off = base + (long)F::template loc<0>(t, g, a) * geo.row_stride;
-      v[g * F::R(0) + a] = x[off];
-      kk[g * F::R(0) + a] = kf[off];
-    }
+    for (int e = 0; e < E; ++e) smx[am(F::template loc<0>(t, e / F::R(0), e % F::R(0)))] = v[e];
+  }
   deriv_inplace<T, N>(v, tw, sm, am, sy, t);
   GLIA_UNROLL
   for (int e = 0; e < E; ++e) { v[e].x *= kk[e].x; v[e].y *= kk[e].y; }
+  // the accumulator tile is fetched now, so that its latency hides behind the second derivative
+  cplx<T> ac[E];
+  if (EPI != EPI_SET) {
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e)
+      ac[e] = acc[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride];
+  }
   deriv_inplace<T, N>(v, tw, sm, am, sy, t);
 
+  if (EPI == EPI_AXPY) {  // out1 += alpha * (acc + D..): loads batched ahead of the stores
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const long off = base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride;
+      const cplx<T> o = out1[off];
+      v[e] = {o.x + alpha * (v[e].x + ac[e].x), o.y + alpha * (v[e].y + ac[e].y)};
+    }
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e)
+      out1[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride] = v[e];
+    return;
+  }
   double dsum[1] = {0.0};
   GLIA_UNROLL
-  for (int g = 0; g < F::Gp(0); ++g)
-    GLIA_UNROLL
-    for (int a = 0; a < F::R(0); ++a) {
-      const int e = g * F::R(0) + a;
-      const long off = base + (long)F::template loc<0>(t, g, a) * geo.row_stride;
-      cplx<T> s = v[e];
-      if (EPI != EPI_SET) { const cplx<T> ac = acc[off]; s.x += ac.x; s.y += ac.y; }
-      if (EPI == EPI_SET || EPI == EPI_ADD) {
-        acc[off] = s;
-      } else if (EPI == EPI_PLAIN) {
-        out1[off] = s;
-      } else if (EPI == EPI_MATVEC) {
-        const cplx<T> xv = x[off];
-        cplx<T> w = {xv.x + alpha * s.x, xv.y + alpha * s.y};
-        out1[off] = w;
-        dsum[0] += (double)xv.x * (double)w.x + (double)xv.y * (double)w.y;
-      } else if (EPI == EPI_RHS) {
-        const cplx<T> xv = x[off];
-        const T ds0 = alpha * s.x, ds1 = alpha * s.y;
-        cplx<T> b = {xv.x + ds0, xv.y + ds1};
-        cplx<T> ax = {xv.x - ds0, xv.y - ds1};
-        out1[off] = b;
-        out2[off] = {b.x - ax.x, b.y - ax.y};
-      } else if (EPI == EPI_AXPY) {
-        cplx<T> o = out1[off];
-        o.x += alpha * s.x; o.y += alpha * s.y;
-        out1[off] = o;
-      }
+  for (int e = 0; e < E; ++e) {
+    const int lc = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+    const long off = base + (long)lc * geo.row_stride;
+    cplx<T> s = v[e];
+    if (EPI != EPI_SET) { s.x += ac[e].x; s.y += ac[e].y; }
+    if (EPI == EPI_SET || EPI == EPI_ADD || EPI == EPI_PLAIN) {
+      out1[off] = s;
+    } else if (EPI == EPI_MATVEC) {
+      const cplx<T> xv = smx[am(lc)];
+      cplx<T> w = {xv.x + alpha * s.x, xv.y + alpha * s.y};
+      out1[off] = w;
+      dsum[0] += (double)xv.x * (double)w.x + (double)xv.y * (double)w.y;
+    } else if (EPI == EPI_RHS) {
+      const cplx<T> xv = smx[am(lc)];
+      const T ds0 = alpha * s.x, ds1 = alpha * s.y;
+      cplx<T> b = {xv.x + ds0, xv.y + ds1};
+      cplx<T> ax = {xv.x - ds0, xv.y - ds1};
+      out1[off] = b;
+      out2[off] = {b.x - ax.x, b.y - ax.y};
     }
+  }
   if (EPI == EPI_MATVEC) block_reduce_store<1>(dsum, partial + (size_t)blockIdx.y * gridDim.x);
 }
 
@@ -180,16 +201,18 @@ ks_deriv1(TileS geo, const cplx<T>* __restrict__ in, cplx<T>* out, const cplx<T>
     GLIA_UNROLL
     for (int a = 0; a < F::R(0); ++a)
       v[g * F::R(0) + a] = in[base + (long)F::template loc<0>(t, g, a) * geo.row_stride];
+  cplx<T> o[E];
+  if (ADD) {  // fetched before the transform so the latency hides behind it
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) o[e] = out[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride];
+  }
   deriv_inplace<T, N>(v, tw, sm, AmS{l}, SyncCta{}, t);
   GLIA_UNROLL
-  for (int g = 0; g < F::Gp(0); ++g)
-    GLIA_UNROLL
-    for (int a = 0; a < F::R(0); ++a) {
-      const long off = base + (long)F::template loc<0>(t, g, a) * geo.row_stride;
-      cplx<T> s = v[g * F::R(0) + a];
-      if (ADD) { const cplx<T> o = out[off]; s.x += o.x; s.y += o.y; }
-      out[off] = s;
-    }
+  for (int e = 0; e < E; ++e) {
+    cplx<T> s = v[e];
+    if (ADD) { s.x += o[e].x; s.y += o[e].y; }
+    out[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride] = s;
+  }
 }
 
 // S-geometry gradient-product sweep: Tk += coef * D(c) . D(p)
@@ -219,16 +242,12 @@ ks_gradprod(TileS geo, const cplx<T>* __restrict__ c, const cplx<T>* __restrict_
   deriv_inplace<T, N>(v, tw, sm, AmS{l}, SyncCta{}, t);
   deriv_inplace<T, N>(u, tw, sm, AmS{l}, SyncCta{}, t);
   GLIA_UNROLL
-  for (int g = 0; g < F::Gp(0); ++g)
-    GLIA_UNROLL
-    for (int a = 0; a < F::R(0); ++a) {
-      const int e = g * F::R(0) + a;
-      const long off = base + (long)F::template loc<0>(t, g, a) * geo.row_stride;
-      cplx<T> o = Tk[off];
-      o.x += coef * (v[e].x * u[e].x);
-      o.y += coef * (v[e].y * u[e].y);
-      Tk[off] = o;
-    }
+  for (int e = 0; e < E; ++e) {  // all loads of Tk first, then all stores
+    const cplx<T> o = Tk[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride];
+    v[e] = {o.x + coef * (v[e].x * u[e].x), o.y + coef * (v[e].y * u[e].y)};
+  }
+  GLIA_UNROLL
+  for (int e = 0; e < E; ++e) Tk[base + (long)F::template loc<0>(t, e / F::R(0), e % F::R(0)) * geo.row_stride] = v[e];
 }
 
 // S-geometry complex transform along the tile axis, in place capable.
@@ -421,18 +440,24 @@ kz_deriv1(LinesZ ln, const T* __restrict__ in, T* out, const cplx<T>* __restrict
       const int pos = F::template loc<0>(z.t, g, a);
       v[g * F::R(0) + a] = {in[la + pos], in[lb + pos]};
     }
+  cplx<T> o[E];
+  if (ADD) {
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      o[e] = {out[la + pos], out[lb + pos]};
+    }
+  }
   deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
-    for (int g = 0; g < F::Gp(0); ++g)
-      GLIA_UNROLL
-      for (int a = 0; a < F::R(0); ++a) {
-        const int pos = F::template loc<0>(z.t, g, a);
-        T ox = v[g * F::R(0) + a].x, oy = v[g * F::R(0) + a].y;
-        if (ADD) { ox += out[la + pos]; oy += out[lb + pos]; }
-        out[la + pos] = ox;
-        out[lb + pos] = oy;
-      }
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      T ox = v[e].x, oy = v[e].y;
+      if (ADD) { ox += o[e].x; oy += o[e].y; }
+      out[la + pos] = ox;
+      out[lb + pos] = oy;
+    }
   }
 }
 
@@ -461,31 +486,37 @@ kz_gradprod(LinesZ ln, const T* __restrict__ c, const T* __restrict__ p, T* Tk, 
       u[g * F::R(0) + a] = {p[la + pos], p[lb + pos]};
     }
   if (Tr && z.active) {
+    cplx<T> o[E];
     GLIA_UNROLL
-    for (int g = 0; g < F::Gp(0); ++g)
-      GLIA_UNROLL
-      for (int a = 0; a < F::R(0); ++a) {
-        const int e = g * F::R(0) + a;
-        const int pos = F::template loc<0>(z.t, g, a);
-        // work = c*c ; work -= c ; work = p*work ; temp += dt*w*work
-        T wa = v[e].x * v[e].x; wa = wa - v[e].x; wa = u[e].x * wa;
-        T wb = v[e].y * v[e].y; wb = wb - v[e].y; wb = u[e].y * wb;
-        Tr[la + pos] += coef * wa;
-        Tr[lb + pos] += coef * wb;
-      }
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      o[e] = {Tr[la + pos], Tr[lb + pos]};
+    }
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      // work = c*c ; work -= c ; work = p*work ; temp += dt*w*work
+      T wa = v[e].x * v[e].x; wa = wa - v[e].x; wa = u[e].x * wa;
+      T wb = v[e].y * v[e].y; wb = wb - v[e].y; wb = u[e].y * wb;
+      Tr[la + pos] = o[e].x + coef * wa;
+      Tr[lb + pos] = o[e].y + coef * wb;
+    }
   }
   deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
   deriv_inplace<T, N>(u, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
-    for (int g = 0; g < F::Gp(0); ++g)
-      GLIA_UNROLL
-      for (int a = 0; a < F::R(0); ++a) {
-        const int e = g * F::R(0) + a;
-        const int pos = F::template loc<0>(z.t, g, a);
-        Tk[la + pos] += coef * (v[e].x * u[e].x);
-        Tk[lb + pos] += coef * (v[e].y * u[e].y);
-      }
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      const T ox = Tk[la + pos], oy = Tk[lb + pos];
+      v[e] = {ox + coef * (v[e].x * u[e].x), oy + coef * (v[e].y * u[e].y)};
+    }
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      Tk[la + pos] = v[e].x;
+      Tk[lb + pos] = v[e].y;
+    }
   }
 }
 

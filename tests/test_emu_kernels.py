@@ -31,8 +31,8 @@ def test_grad_div(B, dtype):
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("sinusoidal", [True, False])
 def test_apply_D(B, dtype, sinusoidal):
-    for e in Cs.case_apply_D(B, 32, dtype, sinusoidal):
-        assert e < 10 * EPS[np.dtype(dtype)]
+    e1, e2, budget = Cs.case_apply_D(B, 32, dtype, sinusoidal)
+    assert e1 < budget and e2 < budget
 
 
 @pytest.mark.parametrize("dtype", DT)

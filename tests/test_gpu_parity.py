@@ -45,13 +45,13 @@ def test_grad_div(B, n, dtype):
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("n,sinusoidal", [(64, True), (64, False), (128, False), (256, False)])
 def test_apply_D(B, n, dtype, sinusoidal):
-    for e in Cs.case_apply_D(B, n, dtype, sinusoidal):
-        assert e < 10 * EPS[np.dtype(dtype)]
+    e1, e2, budget = Cs.case_apply_D(B, n, dtype, sinusoidal)
+    assert e1 < budget and e2 < budget
 
 
 def test_apply_D_512_f32(B):
-    for e in Cs.case_apply_D(B, 512, np.float32, False):
-        assert e < 3e-5
+    e1, e2, budget = Cs.case_apply_D(B, 512, np.float32, False)
+    assert e1 < budget and e2 < budget
 
 
 @pytest.mark.parametrize("dtype", DT)
