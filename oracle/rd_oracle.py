@@ -529,3 +529,79 @@ def test_gaussian(n: int, dtype) -> np.ndarray:
     r = np.sqrt((d[:, None, None] ** 2 + d[None, :, None] ** 2 + d[None, None, :] ** 2).astype(dt)).astype(dt)
     ratio = (r / R).astype(dt)
     return np.exp(-(ratio * ratio)).astype(dt)
+
+
+# --------------------------------------------------------------------------
+# atlas / material properties / Phi  (inputs of the path: c(0) = Phi p)
+# --------------------------------------------------------------------------
+def split_segmentation(seg, labels=(6, 5, 7, 8), dtype=np.float64):
+    """splitSegmentation (src/utils/Utils.cpp:592-657): one-hot maps for
+    labels = [wm, gm, vt, csf] (scripts/forward.py:17 uses wm=6, gm=5, vt=7, csf=8)."""
+    wm_l, gm_l, vt_l, csf_l = labels
+    one = lambda l: (seg == l).astype(dtype) if l > 0 else np.zeros(seg.shape, dtype)
+    return {"wm": one(wm_l), "gm": one(gm_l), "vt": one(vt_l), "csf": one(csf_l)}
+
+
+def read_atlas(maps, n, smoothing_factor=1.0, smoothing_factor_atlas=1.0):
+    """SolverInterface::readAtlas (src/SolverInterface.cpp:502-570): every present tissue
+    map is smoothed with sigma = smoothing_factor * 2 pi / n (order gm, wm, vt, csf)."""
+    out = {}
+    for key in ("gm", "wm", "vt", "csf"):
+        v = maps.get(key)
+        if v is None:
+            out[key] = None
+            continue
+        dt = v.dtype.type
+        sigma = dt(smoothing_factor * 2 * np.pi / n)
+        out[key] = weierstrass_smoother(v, sigma) if smoothing_factor_atlas > 0 else v.copy()
+    return out
+
+
+def mat_prop(atlas, shape, dtype):
+    """MatProp::setValuesCustom (src/mat/MatProp.cpp:135-201): absent maps are zero, clip at
+    0, bg = 1 - sum, filter = (wm > 0.1 or gm > 0.1) and vt < 0.8."""
+    z = lambda k: (np.zeros(shape, dtype) if atlas.get(k) is None else atlas[k].astype(dtype))
+    m = {k: np.where(z(k) <= 0, 0, z(k)).astype(dtype) for k in ("gm", "wm", "vt", "csf")}
+    bg = (m["gm"] + m["wm"]).astype(dtype)
+    bg = (bg + m["vt"]).astype(dtype)
+    bg = (bg + m["csf"]).astype(dtype)
+    m["bg"] = (-(bg - dtype(1.0))).astype(dtype)
+    m["filter"] = (((m["wm"] > 0.1) | (m["gm"] > 0.1)) & (m["vt"] < 0.8)).astype(dtype)
+    return m
+
+
+def phi_apply(p, centers, sigma_phi, filt, smoothing_factor=1.0):
+    """Phi::apply in on-the-fly mode (src/mat/Phi.cpp:264-374): for every non-zero p_i,
+    phi_i = truncate_{5 sigma}( W_sigma( Gaussian_i * filter ) ); out = sum_i p_i phi_i / max_i max(phi_i)."""
+    dt = filt.dtype
+    t = dt.type
+    n0, n1, n2 = filt.shape
+    twopi = t(2.0 * np.pi)
+    hx, hy, hz = t(twopi / n0), t(twopi / n1), t(twopi / n2)
+    sigma_smooth = t(smoothing_factor * 2.0 * np.pi / n0)
+    sig = t(sigma_phi)
+    R = t(np.sqrt(2.0) * float(sig))
+    out = np.zeros(filt.shape, dt)
+    phi_max = t(0)
+    nnz = False
+    X = (hx * np.arange(n0).astype(dt)).astype(dt)
+    Y = (hy * np.arange(n1).astype(dt)).astype(dt)
+    Z = (hz * np.arange(n2).astype(dt)).astype(dt)
+    for pi, ctr in zip(p, centers):
+        if pi == 0:
+            continue
+        nnz = True
+        dx = (X - t(ctr[0]))[:, None, None]
+        dy = (Y - t(ctr[1]))[None, :, None]
+        dz = (Z - t(ctr[2]))[None, None, :]
+        r = np.sqrt((dx * dx + dy * dy + dz * dz).astype(dt)).astype(dt)
+        ratio = (r / R).astype(dt)
+        phi = np.exp(-(ratio * ratio)).astype(dt)
+        phi = (filt * phi).astype(dt)
+        phi = weierstrass_smoother(phi, sigma_smooth)
+        phi = np.where((r / sig) <= 5, phi, 0).astype(dt)
+        phi_max = max(phi_max, t(phi.max()))
+        out = (out + t(pi) * phi).astype(dt)
+    if not nnz:
+        phi_max = t(1)
+    return (out * (t(1.0) / phi_max)).astype(dt)

@@ -186,3 +186,41 @@ def test_error_paths(B):
     with pytest.raises(GliaRdError, match="out of range"):
         h.history_ptr(0, 7)
     h.close()
+
+
+# ---- config 1 of BASELINE.json: test_forward_config.txt inputs (model 1) vs committed golden ----
+@pytest.mark.parametrize("name,dtype", [("f32", np.float32), ("f64", np.float64)])
+def test_config1_brain_forward_adjoint_vs_golden(B, name, dtype):
+    """atlas.nc split + smoothed, one Gaussian at (137,169,96), rho 8, kappa 0.01, nt 25,
+    dt 0.04; expected values generated by tests/golden/make_golden.py from the oracle in the
+    build container (where K2 pins the inputs: ||c0|| = 4.09351)."""
+    from golden import fixtures as FX
+    z = np.load(FX.FWD)
+    P = FX.brain_problem(dtype)
+    n, nt, dt = P["n"], P["nt"], P["dt"]
+    m = P["m"]
+    h = B.handle(n, dtype, dt_ctx=dt)
+    wm, gm, csf = B.put(m["wm"]), B.put(m["gm"]), B.put(m["csf"])
+    h.set_diffusion_tissue(wm, gm, csf, 0.01, 0.0, 0.0, float(m["filter"].sum(dtype=np.float64)))
+    h.set_reaction_tissue(wm, gm, csf, 8.0, 0.0, 0.0)
+    h.prec_factor()
+    h.resize_history(nt, dt)
+    cT = B.empty((n, n, n), dtype)
+    its_s = h.solve_state(B.put(P["c0"]), cT, 0)
+    cTh = B.get(cT)
+    tol = Cs.TOL[np.dtype(dtype)]
+    nrm = lambda a: float(np.sqrt(np.sum(a.astype(np.float64) ** 2)))
+    assert its_s == int(z[f"{name}_its_state"])
+    assert abs(nrm(cTh) - float(z[f"{name}_cT_norm"])) < tol * float(z[f"{name}_cT_norm"])
+    assert Cs.rel(cTh[34, 42, :], z[f"{name}_cT_line"]) < 10 * tol
+    pT = (-(cTh - (0.5 * cTh).astype(dtype))).astype(dtype)
+    p0 = B.empty((n, n, n), dtype)
+    its_a = h.solve_adjoint(B.put(pT), p0, 1, True)
+    p0h = B.get(p0)
+    assert its_a == int(z[f"{name}_its_adj"])
+    assert abs(nrm(p0h) - float(z[f"{name}_p0_norm"])) < 10 * tol * float(z[f"{name}_p0_norm"])
+    assert Cs.rel(p0h[34, 42, :], z[f"{name}_p0_line"]) < 10 * tol
+    g = h.grad_kappa_rho(wm, gm, csf)
+    gr = z[f"{name}_grad"]
+    assert np.max(np.abs(g - gr) / np.maximum(np.abs(gr), 1e-300)) < 20 * tol
+    h.close()
