@@ -22,6 +22,9 @@ SIGNATURES = {
     "glia_rd_abi_version": (_I, []),
     "glia_rd_build_info": (C.c_char_p, []),
     "glia_rd_create": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D]),
+    "glia_rd_create_slab": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D, _I, _I]),
+    "glia_rd_ipc_export": (_I, [_P, _I, _P]),
+    "glia_rd_ipc_connect": (_I, [_P, _I, _P]),
     "glia_rd_destroy": (_I, [_P]),
     "glia_rd_last_error": (C.c_char_p, [_P]),
     "glia_rd_stream": (_P, [_P]),

@@ -44,7 +44,8 @@ const char* glia_rd_build_info(void) {
 #endif
 }
 
-int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx) {
+int glia_rd_create_slab(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx, int rank,
+                        int nranks) {
   if (!out) return 2;
   *out = nullptr;
   glia_rd_t* h = new glia_rd();
@@ -59,8 +60,8 @@ int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, d
     if (device < 0 || device >= ndev) throw EngineError{"device ordinal out of range"};
 #endif
     if (!n) throw EngineError{"n is null"};
-    if (precision == GLIA_RD_F32) h->eng = make_engine_f32(n, device, dt_ctx);
-    else if (precision == GLIA_RD_F64) h->eng = make_engine_f64(n, device, dt_ctx);
+    if (precision == GLIA_RD_F32) h->eng = make_engine_f32(n, device, dt_ctx, rank, nranks);
+    else if (precision == GLIA_RD_F64) h->eng = make_engine_f64(n, device, dt_ctx, rank, nranks);
     else throw EngineError{"precision must be 4 or 8"};
   } catch (const EngineError& e) {
     h->err = e.msg;
@@ -70,6 +71,21 @@ int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, d
     return 1;
   }
   return 0;
+}
+int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx) {
+  return glia_rd_create_slab(out, n, precision, device, dt_ctx, 0, 1);
+}
+int glia_rd_ipc_export(glia_rd_t* h, int which, void* handle64) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!handle64) throw EngineError{"null handle buffer"};
+    E.v_ipc_export(which, (unsigned char*)handle64);
+  });
+}
+int glia_rd_ipc_connect(glia_rd_t* h, int which, const void* handles) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!handles) throw EngineError{"null handle array"};
+    E.v_ipc_connect(which, (const unsigned char*)handles);
+  });
 }
 int glia_rd_destroy(glia_rd_t* h) {
   if (!h) return 0;

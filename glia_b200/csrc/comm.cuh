@@ -1,0 +1,111 @@
+// comm.cuh -- device-side peer communication of the slab-decomposed (multi-GPU) path.
+//
+// The reference distributes the grid with AccFFT: every 3-D FFT crosses ranks through MPI
+// all-to-all transposes and every PETSc VecDot/VecNorm is an MPI_Allreduce
+// (src/grad/SpectralOperators.cpp:80,96,169,253,398-421; KSPCG inside
+// src/pde/DiffusionSolver.cpp:241).  Here one process drives one GPU, every rank maps the
+// other ranks' field arenas (CUDA IPC over NVLink / NVSwitch), and
+//   * the x-axis sweeps read and write their rows directly in the owners' HBM
+//     (sweeps_dist.cuh) -- transform and exchange are one kernel;
+//   * ranks order themselves with flag barriers living in those arenas;
+//   * the PCG scalars are all-reduced by the scalar kernels themselves, summed in rank
+//     order so that every rank takes bit-identical control decisions.
+#pragma once
+#include "simt.h"
+
+namespace glia {
+
+static constexpr int MAX_RANKS = 8;
+static constexpr int RED_NV = 4;  // doubles per reduction slot
+
+// view of the communication block of every rank's arena
+struct Comm {
+  int G = 1, rank = 0;
+  unsigned* flags[MAX_RANKS] = {};  // flags[q][s]: last epoch rank s announced to rank q
+  double* red[MAX_RANKS] = {};      // red[q][(parity*MAX_RANKS + s)*RED_NV + i]
+  int* err = nullptr;               // local: set when a wait timed out
+};
+
+#if defined(GLIA_SIMT_EMU)
+__device__ inline void st_release_sys(unsigned* p, unsigned v) { std::atomic_ref<unsigned>(*p).store(v, std::memory_order_release); }
+__device__ inline unsigned ld_acquire_sys(const unsigned* p) {
+  return std::atomic_ref<unsigned>(*const_cast<unsigned*>(p)).load(std::memory_order_acquire);
+}
+__device__ inline void st_sys(double* p, double v) { std::atomic_ref<double>(*p).store(v, std::memory_order_relaxed); }
+__device__ inline double ld_sys(const double* p) {
+  return std::atomic_ref<double>(*const_cast<double*>(p)).load(std::memory_order_relaxed);
+}
+__device__ inline void fence_sys() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+__device__ inline void spin_pause() { std::this_thread::yield(); }
+#else
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(64); }
+#endif
+
+// thread t < G: announce `epoch` to rank t, then wait until rank t has announced it to us.
+// A rank that never shows up (crashed peer) ends the wait after a bounded number of polls and
+// raises the local error flag instead of hanging the GPU.
+__device__ inline void peer_signal_wait(const Comm& c, unsigned epoch, int t) {
+  fence_sys();
+  st_release_sys(c.flags[t] + c.rank, epoch);
+  const unsigned* mine = c.flags[c.rank] + t;
+  long polls = 0;
+  while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+    spin_pause();
+    if (++polls > (1L << 27)) { *c.err = 1; break; }
+  }
+}
+
+// all ranks: everything enqueued before the barrier on every rank is complete and visible
+static __global__ void k_peer_barrier(Comm c, unsigned epoch) {
+  const int t = threadIdx.x;
+  if (t < c.G) peer_signal_wait(c, epoch, t);
+}
+
+// v <- sum over ranks of v, in rank order, identical on every rank.  Called by all threads of a
+// CTA (>= MAX_RANKS threads); `v` must hold the same values in every thread on entry.
+template <int NV>
+__device__ inline void peer_allreduce(const Comm& c, unsigned epoch, unsigned seq, double (&v)[NV]) {
+  static_assert(NV <= RED_NV, "slot size");
+  if (c.G <= 1) return;
+  __shared__ double sh_red[RED_NV];
+  const int t = threadIdx.x;
+  const int slot = (int)(seq & 1u) * MAX_RANKS;
+  if (t < c.G) {
+    double* dst = c.red[t] + (size_t)(slot + c.rank) * RED_NV;
+    GLIA_UNROLL
+    for (int i = 0; i < NV; ++i) st_sys(dst + i, v[i]);
+    peer_signal_wait(c, epoch, t);
+  }
+  __syncthreads();
+  if (t == 0) {
+    GLIA_UNROLL
+    for (int i = 0; i < NV; ++i) {
+      double s = 0.0;
+      for (int q = 0; q < c.G; ++q) s += ld_sys(c.red[c.rank] + (size_t)(slot + q) * RED_NV + i);
+      sh_red[i] = s;
+    }
+  }
+  __syncthreads();
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) v[i] = sh_red[i];
+  __syncthreads();
+}
+
+}  // namespace glia

@@ -11,6 +11,7 @@
 #include "engine_base.h"
 #include "pointwise.cuh"
 #include "sweeps.cuh"
+#include "sweeps_dist.cuh"
 
 namespace glia {
 
@@ -32,6 +33,20 @@ inline bool is_pinned(const void* p) {
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
+// inter-process shareable device memory (CUDA IPC): the slab ranks map each other's arenas
+inline int ipc_alloc(void** p, size_t n, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  int e = (int)cudaMalloc(p, n ? n : 1);
+  if (e) return e;
+  return (int)cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), *p);
+}
+inline int ipc_open(void** p, const unsigned char handle[64], size_t) {
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  return (int)cudaIpcOpenMemHandle(p, hd, cudaIpcMemLazyEnablePeerAccess);
+}
+inline void ipc_close(void* p, size_t) { if (p) cudaIpcCloseMemHandle(p); }
+inline void ipc_free(void* p, size_t, const unsigned char*) { if (p) cudaFree(p); }
 inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
@@ -121,14 +136,31 @@ class Engine : public EngineBase {
  public:
   using C = cplx<T>;
   int n[3];
-  long nreal, ncplx;
-  int n2c;  // n2/2: complex columns of the pair view
+  // slab decomposition along x (G = 1: the whole grid): this rank owns x-planes
+  // [rank*n0l, (rank+1)*n0l) and sweeps the x lines with y in [rank*n1l, (rank+1)*n1l)
+  int G = 1, rank = 0, n0l, n1l;
+  long nreal, ncplx;  // LOCAL element counts
+  int n2c;            // n2/2: complex columns of the pair view
   cudaStream_t st = 0;
   rt::Timer timer;
   rt::Profiler prof;
 
-  // coefficients
-  T *kf = nullptr, *ktil = nullptr, *rho = nullptr;
+  // one arena holds every field an x sweep of another rank may touch (G > 1: IPC-shared)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  unsigned char arena_handle[64] = {};
+  char* peer_arena[MAX_RANKS] = {};
+  bool connected = false;
+  char* hist_arena = nullptr;
+  size_t hist_bytes = 0;
+  unsigned char hist_handle[64] = {};
+  char* peer_hist[MAX_RANKS] = {};
+  bool hist_connected = false;
+  Comm comm;
+  unsigned epoch = 0, rseq = 0;
+
+  // coefficients (kT, ktilT: pencil copies for the distributed x sweeps)
+  T *kf = nullptr, *ktil = nullptr, *rho = nullptr, *kT = nullptr, *ktilT = nullptr;
   T kavg[3] = {0, 0, 0};
   T k_scale = (T)1e-2;
   T dt_ctx;
@@ -151,30 +183,48 @@ class Engine : public EngineBase {
   T dt = 0;
   T *c_hist = nullptr, *p_hist = nullptr, *chalf_hist = nullptr;
   T *c_t = nullptr, *p_0 = nullptr, *work11 = nullptr, *Tk = nullptr, *Tr = nullptr;
+  T *stage = nullptr, *TkX = nullptr;  // G > 1 only
   // host staging for the host-buffer entry point
   T *hs_in = nullptr, *hs_out = nullptr;
 
   int precision() const override { return (int)sizeof(T); }
 
-  Engine(const int nn[3], int device, double dt_ctx_) {
+  Engine(const int nn[3], int device, double dt_ctx_, int rank_ = 0, int nranks_ = 1) {
     for (int i = 0; i < 3; ++i) {
       n[i] = nn[i];
       if (!(n[i] == 32 || n[i] == 64 || n[i] == 128 || n[i] == 256 || n[i] == 512))
         throw EngineError{"grid sizes must be powers of two in [32, 512]"};
     }
+    G = nranks_;
+    rank = rank_;
+    if (!(G == 1 || G == 2 || G == 4 || G == 8) || rank < 0 || rank >= G)
+      throw EngineError{"slab ranks: nranks must be 1, 2, 4 or 8 and 0 <= rank < nranks"};
+    n0l = n[0] / G;
+    n1l = n[1] / G;
+    if (n0l < 1 || n1l < 1 || (long)n0l * n[1] < 2) throw EngineError{"grid too small for this many slabs"};
     GLIA_CHECK(rt::set_device(device));
     GLIA_CHECK(rt::stream_create(&st));
     timer.create();
-    nreal = (long)n[0] * n[1] * n[2];
+    nreal = (long)n0l * n[1] * n[2];
     ncplx = nreal / 2;
     n2c = n[2] / 2;
     dt_ctx = (T)dt_ctx_;
-    T** fields[] = {&kf, &ktil, &rho, &b, &r, &z, &p, &w, &acc, &c_t, &p_0, &work11, &Tk, &Tr};
-    for (T** f : fields) {
-      GLIA_CHECK(rt::dev_malloc((void**)f, sizeof(T) * nreal));
-      GLIA_CHECK(rt::zero(*f, sizeof(T) * nreal, st));
-    }
-    GLIA_CHECK(rt::dev_malloc((void**)&shat, sizeof(C) * ncplx));
+    std::vector<T**> fields = {&kf, &ktil, &rho, &b, &r, &z, &p, &w, &acc, &c_t, &p_0, &work11, &Tk, &Tr};
+    if (G > 1) { fields.push_back(&kT); fields.push_back(&ktilT); fields.push_back(&stage); fields.push_back(&TkX); }
+    const size_t fbytes = sizeof(T) * nreal;  // a multiple of 256 bytes for every admissible grid
+    const size_t comm_bytes = 4096;
+    arena_bytes = fbytes * (fields.size() + 1) + comm_bytes;
+    if (G > 1) GLIA_CHECK(rt::ipc_alloc((void**)&arena, arena_bytes, arena_handle));
+    else GLIA_CHECK(rt::dev_malloc((void**)&arena, arena_bytes));
+    GLIA_CHECK(rt::zero(arena, arena_bytes, st));
+    size_t off = 0;
+    for (T** f : fields) { *f = reinterpret_cast<T*>(arena + off); off += fbytes; }
+    shat = reinterpret_cast<C*>(arena + off); off += fbytes;
+    // communication block: flags[MAX_RANKS] then the reduction slots
+    comm.G = G;
+    comm.rank = rank;
+    peer_arena[rank] = arena;
+    bind_comm(off);
     for (int a = 0; a < 3; ++a) {
       std::vector<C> tab(n[a]);
       for (int j = 0; j < n[a]; ++j) {
@@ -192,6 +242,7 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::dev_malloc((void**)&iscal, sizeof(int) * I_NISCAL));
     GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL, st));
     GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL, st));
+    comm.err = iscal + I_COMM_ERR;
     GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * I_NISCAL));
     GLIA_CHECK(rt::host_malloc((void**)&h_out, sizeof(double) * 16));
     sym = PcSym<T>{dt_ctx, (T)0, (T)0, (T)0, (T)(1.0 / ((double)n[0] * n[1] * n[2]))};
@@ -199,9 +250,13 @@ class Engine : public EngineBase {
   }
   ~Engine() override {
     rt::sync(st);
-    T* fields[] = {kf, ktil, rho, b, r, z, p, w, acc, c_t, p_0, work11, Tk, Tr, c_hist, p_hist, chalf_hist};
-    for (T* f : fields) rt::dev_free(f);
-    rt::dev_free(shat);
+    for (int q = 0; q < G; ++q) {
+      if (q == rank) continue;
+      if (peer_arena[q]) rt::ipc_close(peer_arena[q], arena_bytes);
+      if (peer_hist[q]) rt::ipc_close(peer_hist[q], hist_bytes);
+    }
+    if (G > 1) { rt::ipc_free(arena, arena_bytes, arena_handle); rt::ipc_free(hist_arena, hist_bytes, hist_handle); }
+    else { rt::dev_free(arena); rt::dev_free(hist_arena); }
     for (int a = 0; a < 3; ++a) rt::dev_free(tw[a]);
     rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal);
     rt::host_free(h_iscal); rt::host_free(h_out);
@@ -209,6 +264,76 @@ class Engine : public EngineBase {
     timer.destroy();
     prof.destroy();
     rt::stream_destroy(st);
+  }
+
+  // ------------------------------------------------------- slab plumbing ----
+  size_t comm_off = 0;
+  void bind_comm(size_t off) {
+    comm_off = off;
+    for (int q = 0; q < G; ++q) {
+      if (!peer_arena[q]) continue;
+      comm.flags[q] = reinterpret_cast<unsigned*>(peer_arena[q] + off);
+      comm.red[q] = reinterpret_cast<double*>(peer_arena[q] + off + 256);
+    }
+  }
+  void ipc_export(int which, unsigned char out[64]) {
+    if (G <= 1) throw EngineError{"ipc_export: not a slab handle"};
+    if (which == 1 && !hist_arena) throw EngineError{"ipc_export: resize_history() first"};
+    std::memcpy(out, which == 0 ? arena_handle : hist_handle, 64);
+  }
+  // handles: nranks * 64 bytes, rank order (every rank passes the same array)
+  void ipc_connect(int which, const unsigned char* handles) {
+    if (G <= 1) throw EngineError{"ipc_connect: not a slab handle"};
+    sync();
+    char** peers = which == 0 ? peer_arena : peer_hist;
+    const size_t bytes = which == 0 ? arena_bytes : hist_bytes;
+    for (int q = 0; q < G; ++q) {
+      if (q == rank) continue;
+      if (peers[q]) { rt::ipc_close(peers[q], bytes); peers[q] = nullptr; }
+      void* m = nullptr;
+      GLIA_CHECK(rt::ipc_open(&m, handles + 64 * (size_t)q, bytes));
+      peers[q] = (char*)m;
+    }
+    if (which == 0) { bind_comm(comm_off); connected = true; }
+    else hist_connected = true;
+  }
+  bool in_arena(const void* ptr) const {
+    return (const char*)ptr >= arena && (const char*)ptr < arena + arena_bytes;
+  }
+  bool in_hist(const void* ptr) const {
+    return hist_arena && (const char*)ptr >= hist_arena && (const char*)ptr < hist_arena + hist_bytes;
+  }
+  // the same field in every rank's arena (or history arena)
+  PeerRows<T> rows(const T* f) const {
+    PeerRows<T> pr{};
+    if (in_arena(f)) {
+      if (!connected) throw EngineError{"slab handle is not connected (glia_rd_ipc_connect)"};
+      const size_t off = (const char*)f - arena;
+      for (int q = 0; q < G; ++q) pr.base[q] = reinterpret_cast<C*>(peer_arena[q] + off);
+    } else if (in_hist(f)) {
+      if (!hist_connected) throw EngineError{"slab histories are not connected (glia_rd_ipc_connect)"};
+      const size_t off = (const char*)f - hist_arena;
+      for (int q = 0; q < G; ++q) pr.base[q] = reinterpret_cast<C*>((q == rank ? hist_arena : peer_hist[q]) + off);
+    } else {
+      throw EngineError{"internal: x sweep on a field outside the shared arenas"};
+    }
+    return pr;
+  }
+  TileX tile_xd() const {
+    int sh = 0;
+    while ((1 << sh) < n0l) ++sh;
+    return TileX{(long)n[1] * n2c, (long)n2c, (long)n1l * n2c, n2c / SL, n1l, rank * n1l, sh, n0l - 1};
+  }
+  static dim3 grid_xd(const TileX& g) { return dim3(g.nchunk * g.n_outer); }
+  unsigned next_epoch() { return ++epoch; }
+  void barrier() {
+    if (G > 1) L("k_peer_barrier", k_peer_barrier, dim3(1), dim3(32), 0, st, comm, next_epoch());
+  }
+  void build_pencil(const T* slab_field, T* pencil) {
+    barrier();
+    L("k_slab_to_pencil", k_slab_to_pencil<T>, grid_pw(ncplx), dim3(256), 0, st, tile_xd(), n[0], rows(slab_field),
+      (C*)pencil);
+    barrier();
   }
 
   // every kernel launch of the engine goes through here: counted, and (when profiling is on)
@@ -228,9 +353,9 @@ class Engine : public EngineBase {
   void sync() { GLIA_CHECK(rt::sync(st)); check_launch(); }
 
   // ------------------------------------------------------------ geometry ----
-  TileS tile_y() const { return TileS{(long)n2c, (long)n[1] * n2c, n2c / SL, n[0], 0}; }
+  TileS tile_y() const { return TileS{(long)n2c, (long)n[1] * n2c, n2c / SL, n0l, 0}; }
   TileS tile_x() const { return TileS{(long)n[1] * n2c, (long)n2c, n2c / SL, n[1], 0}; }
-  LinesZ lines_z() const { return LinesZ{(long)n[0] * n[1] / 2}; }
+  LinesZ lines_z() const { return LinesZ{(long)n0l * n[1] / 2}; }
   template <int N> static size_t smem_s() { return sizeof(C) * N * SL; }
   template <int N> static size_t smem_s2() { return 2 * sizeof(C) * N * SL; }  // + the kept x tile
   template <int N> static size_t smem_z() { return sizeof(C) * zlines<N>() * zpad<N>(); }
@@ -249,8 +374,31 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------ sweeps ----
   // acc = Dz(k Dz x); acc += Dy(k Dy x); then the x sweep with epilogue EPI
+  // slab-decomposed form: the x sweep runs first, straight on the owners' memory, between two
+  // rank barriers; the z sweep adds to it and the y sweep carries the epilogue.
+  template <int EPI>
+  int dapply_dist(const T* x, const T* kfield, T alpha, T* out1, T* out2, double* pp, const int* done) {
+    const T* kpen = (kfield == kf) ? kT : ktilT;
+    const TileX txd = tile_xd();
+    const TileS ty = tile_y();
+    const PeerRows<T> xr = rows(x), ar = rows(acc);
+    barrier();
+    GLIA_DISPATCH_N(n[0], L("kx_deriv2_dist", kx_deriv2_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, xr,
+                                       (const C*)kpen, ar, (const C*)tw[0], done));
+    barrier();
+    GLIA_DISPATCH_N(n[2], L("kz_deriv2.add", kz_deriv2<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                       lines_z(), x, kfield, acc, (const C*)tw[2], done));
+    const char* ytag = EPI == EPI_MATVEC ? "ks_deriv2.y.matvec" : (EPI == EPI_RHS ? "ks_deriv2.y.rhs" : "ks_deriv2.y.epi");
+    constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
+    GLIA_DISPATCH_N(n[1], L(ytag, ks_deriv2<T, N, EPI>, grid_s(ty), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, ty,
+                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[1], alpha, (C*)out1,
+                                       (C*)out2, pp, done));
+    return (int)grid_s(ty).x;
+  }
+
   template <int EPI>
   int dapply(const T* x, const T* kfield, T alpha, T* out1, T* out2, double* pp, const int* done) {
+    if (G > 1) return dapply_dist<EPI>(x, kfield, alpha, out1, out2, pp, done);
     GLIA_DISPATCH_N(n[2], L("kz_deriv2", kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                        lines_z(), x, kfield, acc, (const C*)tw[2], done));
     const TileS ty = tile_y(), tx = tile_x();
@@ -279,8 +427,17 @@ class Engine : public EngineBase {
     }
     GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
-    GLIA_DISPATCH_N(n[0], L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
-                                       (const C*)tw[0], sym, n[1], done));
+    if (G > 1) {
+      const TileX txd = tile_xd();
+      const PeerRows<T> sr = rows((const T*)shat);
+      barrier();
+      GLIA_DISPATCH_N(n[0], L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr,
+                                         (const C*)tw[0], sym, n[1], done));
+      barrier();
+    } else {
+      GLIA_DISPATCH_N(n[0], L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
+                                         (const C*)tw[0], sym, n[1], done));
+    }
     GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
     GLIA_DISPATCH_N(n[2], {
@@ -302,7 +459,15 @@ class Engine : public EngineBase {
       GLIA_DISPATCH_N(n[1], L("ks_deriv1.y", ks_deriv1<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                          (const C*)x, (C*)gy, (const C*)tw[1]));
     }
-    if ((mask & 1) && gx) {
+    if (G > 1) {  // collective: every rank takes part in the x exchange, whatever its mask
+      const TileX txd = tile_xd();
+      GLIA_CHECK(rt::copy(stage, x, sizeof(T) * nreal, st));
+      barrier();
+      GLIA_DISPATCH_N(n[0], L("kx_deriv1_dist", kx_deriv1_dist<T, N, 0>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd,
+                                         rows(stage), rows(acc), (const C*)tw[0]));
+      barrier();
+      if ((mask & 1) && gx) GLIA_CHECK(rt::copy(gx, acc, sizeof(T) * nreal, st));
+    } else if ((mask & 1) && gx) {
       GLIA_DISPATCH_N(n[0], L("ks_deriv1.x", ks_deriv1<T, N, 0>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
                                          (const C*)x, (C*)gx, (const C*)tw[0]));
     }
@@ -310,12 +475,23 @@ class Engine : public EngineBase {
   }
   void divergence(T* div, const T* dx, const T* dy, const T* dz) {
     const TileS ty = tile_y(), tx = tile_x();
+    T* out = G > 1 ? acc : div;
     GLIA_DISPATCH_N(n[2], L("kz_deriv1", kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                       lines_z(), dz, div, (const C*)tw[2]));
+                                       lines_z(), dz, out, (const C*)tw[2]));
     GLIA_DISPATCH_N(n[1], L("ks_deriv1.y", ks_deriv1<T, N, 1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
-                                       (const C*)dy, (C*)div, (const C*)tw[1]));
-    GLIA_DISPATCH_N(n[0], L("ks_deriv1.x", ks_deriv1<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
-                                       (const C*)dx, (C*)div, (const C*)tw[0]));
+                                       (const C*)dy, (C*)out, (const C*)tw[1]));
+    if (G > 1) {
+      const TileX txd = tile_xd();
+      GLIA_CHECK(rt::copy(stage, dx, sizeof(T) * nreal, st));
+      barrier();
+      GLIA_DISPATCH_N(n[0], L("kx_deriv1_dist", kx_deriv1_dist<T, N, 1>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd,
+                                         rows(stage), rows(acc), (const C*)tw[0]));
+      barrier();
+      GLIA_CHECK(rt::copy(div, acc, sizeof(T) * nreal, st));
+    } else {
+      GLIA_DISPATCH_N(n[0], L("ks_deriv1.x", ks_deriv1<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                         (const C*)dx, (C*)div, (const C*)tw[0]));
+    }
     sync();
   }
 
@@ -324,12 +500,14 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::copy(kf, k, sizeof(T) * nreal, st));
     for (int i = 0; i < 3; ++i) kavg[i] = (T)ka[i];
     k_scale = (T)kscale;
+    if (G > 1) build_pencil(kf, kT);
     sync();
   }
   void field_sum4(const T* t, const T* m0, const T* m1, const T* m2, double out[4]) {
     const dim3 g = grid_pw(nreal);
     L("k_dot3", k_dot3<T>, g, dim3(256), 0, st, nreal, t, m0, m1, m2, part(0));
-    L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8);
+    L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8, comm,
+      G > 1 ? next_epoch() : 0u, rseq++);
     GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
     sync();
     for (int i = 0; i < 4; ++i) out[i] = h_out[i];
@@ -352,6 +530,7 @@ class Engine : public EngineBase {
     const T favg = (T)filter_sum;
     const T kav = ksum * ((T)1.0 / favg);
     kavg[0] = kavg[1] = kavg[2] = kav;
+    if (G > 1) { build_pencil(kf, kT); sync(); }
   }
   void set_reaction_tissue(const T* wm, const T* gm, const T* csf, double rs, double rgm, double rglm) {
     T dr_gm = (T)rs * (T)rgm, dr_wm = (T)rs, dr_glm = (T)rs * (T)rglm;
@@ -365,7 +544,7 @@ class Engine : public EngineBase {
   }
   void apply_D(T* dc, const T* c, bool secondary) {
     const T* src = c;
-    if (dc == c) {  // the reference allows aliasing (PdeOperators.cpp:210)
+    if (dc == c || (G > 1 && !in_arena(c))) {  // the reference allows aliasing (PdeOperators.cpp:210)
       GLIA_CHECK(rt::copy(work11, c, sizeof(T) * nreal, st));
       src = work11;
     }
@@ -384,6 +563,7 @@ class Engine : public EngineBase {
   void fetch_iscal() {
     GLIA_CHECK(rt::d2h(h_iscal, iscal, sizeof(int) * I_NISCAL, st));
     sync();
+    if (h_iscal[I_COMM_ERR]) throw EngineError{"slab peer did not arrive at a rank barrier (timed out)"};
   }
 
   // one PCG iteration, enqueued without synchronisation; `it` is 1-based
@@ -391,15 +571,23 @@ class Engine : public EngineBase {
     const int* done = iscal + I_DONE;
     const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
     const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
-    L("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal);
+    L("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal, comm,
+      G > 1 ? next_epoch() : 0u, rseq++);
     const int nb2 = pc_apply(r, w, z, true, part(1), done);
-    L("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol);
+    L("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
+      comm, G > 1 ? next_epoch() : 0u, rseq++);
     L("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
                  (const int*)iscal, it);
   }
 
   // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.
   int diffusion_solve(T* x, double dt_in) {
+    if (G > 1 && !in_arena(x)) {  // the rhs x sweep reads x through the peer mappings
+      GLIA_CHECK(rt::copy(stage, x, sizeof(T) * nreal, st));
+      const int its = diffusion_solve(stage, dt_in);
+      GLIA_CHECK(rt::copy(x, stage, sizeof(T) * nreal, st));
+      return its;
+    }
     const T dts = (T)dt_in;
     dt_ctx = dts;  // side effect on later prec_factor() calls (trap T2)
     if (k_scale == (T)0) return 0;
@@ -408,7 +596,7 @@ class Engine : public EngineBase {
     const int nb0 = pc_apply(b, nullptr, nullptr, false, part(2), nullptr);
     const int nb1 = pc_apply(r, nullptr, p, true, part(1), nullptr);
     L("k_pcg_init", k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
-                 scal, iscal, rtol, abstol);
+                 scal, iscal, rtol, abstol, comm, G > 1 ? next_epoch() : 0u, rseq++);
     int it = 0;
     // speculate: enqueue as many iterations as the previous solve needed, then look
     int burst = its_guess < 1 ? 1 : its_guess;
@@ -429,16 +617,23 @@ class Engine : public EngineBase {
   // ------------------------------------------------------------ L2a API ----
   void resize_history(int nt_, double dt_) {
     sync();
-    rt::dev_free(c_hist); rt::dev_free(p_hist); rt::dev_free(chalf_hist);
+    for (int q = 0; q < G; ++q)
+      if (q != rank && peer_hist[q]) { rt::ipc_close(peer_hist[q], hist_bytes); peer_hist[q] = nullptr; }
+    hist_connected = false;
+    if (G > 1) rt::ipc_free(hist_arena, hist_bytes, hist_handle);
+    else rt::dev_free(hist_arena);
+    hist_arena = nullptr;
     c_hist = p_hist = chalf_hist = nullptr;
     nt = nt_;
     dt = (T)dt_;
-    GLIA_CHECK(rt::dev_malloc((void**)&c_hist, sizeof(T) * nreal * (nt + 1)));
-    GLIA_CHECK(rt::dev_malloc((void**)&p_hist, sizeof(T) * nreal * (nt + 1)));
-    GLIA_CHECK(rt::dev_malloc((void**)&chalf_hist, sizeof(T) * nreal * (nt > 0 ? nt : 1)));
-    GLIA_CHECK(rt::zero(c_hist, sizeof(T) * nreal * (nt + 1), st));
-    GLIA_CHECK(rt::zero(p_hist, sizeof(T) * nreal * (nt + 1), st));
-    GLIA_CHECK(rt::zero(chalf_hist, sizeof(T) * nreal * (nt > 0 ? nt : 1), st));
+    const size_t fb = sizeof(T) * nreal;
+    hist_bytes = fb * ((size_t)(nt + 1) * 2 + (size_t)(nt > 0 ? nt : 1));
+    if (G > 1) GLIA_CHECK(rt::ipc_alloc((void**)&hist_arena, hist_bytes, hist_handle));
+    else GLIA_CHECK(rt::dev_malloc((void**)&hist_arena, hist_bytes));
+    c_hist = reinterpret_cast<T*>(hist_arena);
+    p_hist = reinterpret_cast<T*>(hist_arena + fb * (size_t)(nt + 1));
+    chalf_hist = reinterpret_cast<T*>(hist_arena + fb * (size_t)(nt + 1) * 2);
+    GLIA_CHECK(rt::zero(hist_arena, hist_bytes, st));
     sync();
   }
   T* hist(int which, int i) {
@@ -508,6 +703,7 @@ class Engine : public EngineBase {
     if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
     GLIA_CHECK(rt::zero(Tk, sizeof(T) * nreal, st));
     GLIA_CHECK(rt::zero(Tr, sizeof(T) * nreal, st));
+    if (G > 1) { GLIA_CHECK(rt::zero(TkX, sizeof(T) * nreal, st)); barrier(); }  // peers' histories complete
     const TileS ty = tile_y(), tx = tile_x();
     for (int i = 0; i <= nt; ++i) {
       const T wgt = (i == 0 || i == nt) ? (T)0.5 : (T)1.0;
@@ -518,8 +714,20 @@ class Engine : public EngineBase {
                                          lines_z(), ci, pi, Tk, Tr, coef, (const C*)tw[2]));
       GLIA_DISPATCH_N(n[1], L("ks_gradprod.y", ks_gradprod<T, N>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                          (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[1]));
-      GLIA_DISPATCH_N(n[0], L("ks_gradprod.x", ks_gradprod<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
-                                         (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[0]));
+      if (G > 1) {  // x part: rows fetched from the owners' histories, accumulated in the pencil layout
+        const TileX txd = tile_xd();
+        GLIA_DISPATCH_N(n[0], L("kx_gradprod_dist", kx_gradprod_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st,
+                                           txd, rows(ci), rows(pi), (C*)TkX, coef, (const C*)tw[0]));
+      } else {
+        GLIA_DISPATCH_N(n[0], L("ks_gradprod.x", ks_gradprod<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                           (const C*)ci, (const C*)pi, (C*)Tk, coef, (const C*)tw[0]));
+      }
+    }
+    if (G > 1) {
+      barrier();
+      L("k_pencil_add_to_slab", k_pencil_add_to_slab<T>, grid_pw(ncplx), dim3(256), 0, st, tile_xd(), n[0], (const C*)TkX,
+        rows(Tk));
+      barrier();
     }
     const double leb = (2.0 * M_PI / n[0]) * (2.0 * M_PI / n[1]) * (2.0 * M_PI / n[2]);
     double s[4];
@@ -569,8 +777,16 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------- type-erased face ----
   void* stream_handle() override { return (void*)(intptr_t)st; }
-  void v_fft_r2c(const void* f, void* fhat) override { fft3d_r2c(*this, (const T*)f, (C*)fhat); }
-  void v_fft_c2r(const void* fhat, void* f) override { fft3d_c2r(*this, (const C*)fhat, (T*)f); }
+  void v_fft_r2c(const void* f, void* fhat) override {
+    if (G > 1) throw EngineError{"glia_rd_fft_r2c: the stand-alone 3-D FFT is single-GPU; slab handles transform inside the sweeps"};
+    fft3d_r2c(*this, (const T*)f, (C*)fhat);
+  }
+  void v_fft_c2r(const void* fhat, void* f) override {
+    if (G > 1) throw EngineError{"glia_rd_fft_c2r: the stand-alone 3-D FFT is single-GPU; slab handles transform inside the sweeps"};
+    fft3d_c2r(*this, (const C*)fhat, (T*)f);
+  }
+  void v_ipc_export(int which, unsigned char* out) override { ipc_export(which, out); }
+  void v_ipc_connect(int which, const unsigned char* handles) override { ipc_connect(which, handles); }
   void v_gradient(void* gx, void* gy, void* gz, const void* x, int m) override {
     gradient((T*)gx, (T*)gy, (T*)gz, (const T*)x, m);
   }
@@ -584,6 +800,7 @@ class Engine : public EngineBase {
   }
   void v_set_secondary_k(const void* kt) override {
     GLIA_CHECK(rt::copy(ktil, kt, sizeof(T) * nreal, st));
+    if (G > 1) build_pencil(ktil, ktilT);
     sync();
   }
   void v_set_reaction(const void* rh) override {

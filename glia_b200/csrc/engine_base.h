@@ -17,6 +17,8 @@ class EngineBase {
   long long launches = 0;
   virtual int precision() const = 0;
   virtual void* stream_handle() = 0;
+  virtual void v_ipc_export(int which, unsigned char* out64) = 0;
+  virtual void v_ipc_connect(int which, const unsigned char* handles) = 0;
   virtual void v_fft_r2c(const void* f, void* fhat) = 0;
   virtual void v_fft_c2r(const void* fhat, void* f) = 0;
   virtual void v_gradient(void* gx, void* gy, void* gz, const void* x, int mask) = 0;
@@ -45,7 +47,7 @@ class EngineBase {
   virtual void v_forward_adjoint(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
   virtual void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
 };
-EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx);
-EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx);
+EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx, int rank, int nranks);
+EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks);
 
 }  // namespace glia

@@ -2,5 +2,7 @@
 #include "engine.cuh"
 #include "spectral3d.cuh"
 namespace glia {
-EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx) { return new Engine<double>(n, device, dt_ctx); }
+EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks) {
+  return new Engine<double>(n, device, dt_ctx, rank, nranks);
+}
 }  // namespace glia

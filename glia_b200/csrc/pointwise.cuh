@@ -1,6 +1,7 @@
 // pointwise.cuh -- streaming kernels of the RD path: logistic reaction, PCG vector
 // updates, device-resident PCG scalars, reductions.
 #pragma once
+#include "comm.cuh"
 #include "fft_core.cuh"
 
 namespace glia {
@@ -12,7 +13,7 @@ __device__ __forceinline__ bool g_isinf(T x) { return x == x && (x - x) != (x - 
 
 // ---- device-resident PCG state (one block per solver handle) --------------
 enum { S_BETA = 0, S_BETAOLD, S_A, S_B, S_DP, S_RNORM0, S_TTOL, S_DPI, S_NSCAL = 16 };
-enum { I_ITS = 0, I_DONE, I_TOTAL, I_REASON, I_NISCAL = 8 };
+enum { I_ITS = 0, I_DONE, I_TOTAL, I_REASON, I_COMM_ERR, I_NISCAL = 8 };
 // reasons follow PETSc's KSPConvergedReason values
 enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_DIVERGED_ITS = -3, KSP_DIVERGED_DTOL = -4,
        KSP_DIVERGED_NANORINF = -9, KSP_DIVERGED_INDEFINITE_MAT = -10 };
@@ -45,10 +46,15 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ partial,
 // KSPConvergedDefault at iteration 0 with a non-zero initial guess:
 //   rnorm0 = ||M^-1 b|| (or dp if that is 0), ttol = max(rtol*rnorm0, abstol), test dp <= ttol.
 static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
-                           double rtol, double abstol) {
+                           double rtol, double abstol, Comm comm, unsigned epoch, unsigned seq) {
   double b[2], rz[2];
   sum_partials<2>(pb, nb, b);
   sum_partials<2>(prz, nrz, rz);
+  {
+    double all[4] = {b[0], b[1], rz[0], rz[1]};
+    peer_allreduce<4>(comm, epoch, seq, all);
+    b[0] = all[0]; b[1] = all[1]; rz[0] = all[2]; rz[1] = all[3];
+  }
   if (threadIdx.x == 0) {
     const double dp = sqrt(rz[0]);
     double rnorm0 = sqrt(b[0]);
@@ -67,10 +73,12 @@ static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, i
 
 // a = beta / <p, A p>
 template <typename T>
-__global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal) {
+__global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal, Comm comm, unsigned epoch,
+                            unsigned seq) {
   if (iscal[I_DONE]) return;
   double d[1];
   sum_partials<1>(ppw, n, d);
+  peer_allreduce<1>(comm, epoch, seq, d);
   if (threadIdx.x == 0) {
     scal[S_DPI] = d[0];
     scal[S_BETAOLD] = scal[S_BETA];
@@ -81,10 +89,12 @@ __global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal) 
 
 // after z = M^-1 r: dp = ||z||, its++, convergence test, beta = <r,z>, b = beta/betaold
 template <typename T>
-__global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, int maxit, double dtol) {
+__global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, int maxit, double dtol, Comm comm,
+                           unsigned epoch, unsigned seq) {
   if (iscal[I_DONE]) return;
   double rz[2];
   sum_partials<2>(prz, n, rz);
+  peer_allreduce<2>(comm, epoch, seq, rz);
   if (threadIdx.x == 0) {
     const double dp = sqrt(rz[0]);
     scal[S_DP] = dp;
@@ -204,9 +214,10 @@ __global__ void k_dot3(long n, const T* __restrict__ t, const T* __restrict__ m0
     partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
   }
 }
-static __global__ void k_sum4(const double* partial, int n, double* out) {
+static __global__ void k_sum4(const double* partial, int n, double* out, Comm comm, unsigned epoch, unsigned seq) {
   double o[4];
   sum_partials<4>(partial, n, o);
+  peer_allreduce<4>(comm, epoch, seq, o);
   if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3]; }
 }
 

@@ -379,8 +379,9 @@ struct ZCtx {
   __device__ __forceinline__ AmZ am() const { return AmZ{lp * zpad<N>()}; }
 };
 
-// Z-geometry second derivative: acc = D_z(k D_z x)  (first sweep of applyD)
-template <typename T, int N>
+// Z-geometry second derivative: acc (+)= D_z(k D_z x)  (first sweep of applyD; ADD: second
+// sweep of the slab-decomposed applyD, whose x sweep runs first)
+template <typename T, int N, int ADD = 0>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, const cplx<T>* __restrict__ twt,
           const int* __restrict__ done) {
@@ -406,6 +407,13 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
   deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
   GLIA_UNROLL
   for (int e = 0; e < E; ++e) { v[e].x *= kk[e].x; v[e].y *= kk[e].y; }
+  if (ADD) {  // the accumulator is fetched now so that its latency hides behind the second derivative
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(z.t, e / F::R(0), e % F::R(0));
+      kk[e] = {acc[la + pos], acc[lb + pos]};
+    }
+  }
   deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
@@ -413,8 +421,10 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
       GLIA_UNROLL
       for (int a = 0; a < F::R(0); ++a) {
         const int pos = F::template loc<0>(z.t, g, a);
-        acc[la + pos] = v[g * F::R(0) + a].x;
-        acc[lb + pos] = v[g * F::R(0) + a].y;
+        cplx<T> s = v[g * F::R(0) + a];
+        if (ADD) { s.x += kk[g * F::R(0) + a].x; s.y += kk[g * F::R(0) + a].y; }
+        acc[la + pos] = s.x;
+        acc[lb + pos] = s.y;
       }
   }
 }

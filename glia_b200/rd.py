@@ -31,40 +31,71 @@ def _ptr(x):
 
 
 class RDHandle:
-    def __init__(self, n, precision="f32", device=0, dt_ctx=0.5, lib_path=None):
+    """``glia_rd_t``.  With ``nranks > 1`` this is one rank of a slab-decomposed handle
+    (``glia_rd_create_slab``): ``n`` is the global grid, every field is this rank's local block
+    ``[n0/nranks][n1][n2]``, every method is collective, and ``all_gather`` -- a callable
+    ``bytes -> list[bytes]`` in rank order, e.g. built on ``torch.distributed.all_gather_object``
+    -- carries the 64-byte IPC handles between the ranks at set-up."""
+
+    def __init__(self, n, precision="f32", device=0, dt_ctx=0.5, lib_path=None, rank=0, nranks=1, all_gather=None):
         self.lib = _capi.load_library(lib_path)
         self.n = tuple(int(v) for v in (n if hasattr(n, "__len__") else (n, n, n)))
         self.precision = {"f32": 4, "f64": 8, 4: 4, 8: 8}[precision]
         self.np_dtype = np.float32 if self.precision == 4 else np.float64
+        self.rank, self.nranks, self._all_gather = int(rank), int(nranks), all_gather
+        if self.nranks > 1 and all_gather is None:
+            raise ValueError("a slab handle needs all_gather(bytes) -> list[bytes] to exchange its IPC handles")
         self._h = C.c_void_p()
         arr = (C.c_int * 3)(*self.n)
-        rc = self.lib.glia_rd_create(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx))
+        rc = self.lib.glia_rd_create_slab(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx),
+                                          self.rank, self.nranks)
         if rc != 0:
             msg = self.lib.glia_rd_last_error(self._h).decode() if self._h else "create failed"
             if self._h:
                 self.lib.glia_rd_destroy(self._h)
                 self._h = C.c_void_p()
             raise _capi.GliaRdError(msg)
+        if self.nranks > 1:
+            self._connect(0)
+
+    def _connect(self, which):
+        """collective: export this rank's arena, gather everybody's, map the peers."""
+        mine = C.create_string_buffer(64)
+        self._ck(self.lib.glia_rd_ipc_export(self._h, int(which), mine))
+        blobs = self._all_gather(mine.raw)
+        assert len(blobs) == self.nranks and all(len(b) == 64 for b in blobs)
+        allh = C.create_string_buffer(b"".join(blobs), 64 * self.nranks)
+        self._ck(self.lib.glia_rd_ipc_connect(self._h, int(which), allh))
+        self._all_gather(b"ok")  # nobody proceeds before every rank has mapped its peers
+
+    @property
+    def local_shape(self):
+        return (self.n[0] // self.nranks, self.n[1], self.n[2])
 
     # -- plumbing ---------------------------------------------------------------
     def _ck(self, rc):
         if rc != 0:
             raise _capi.GliaRdError(self.lib.glia_rd_last_error(self._h).decode())
 
-    def close(self):
+    def close(self, collective=True):
         if getattr(self, "_h", None):
+            if collective and getattr(self, "nranks", 1) > 1 and self._all_gather is not None:
+                try:
+                    self._all_gather(b"bye")  # peers must stop touching this arena before it is freed
+                except Exception:
+                    pass
             self.lib.glia_rd_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
     @property
     def nreal(self):
-        return self.n[0] * self.n[1] * self.n[2]
+        return self.n[0] * self.n[1] * self.n[2] // self.nranks
 
     @property
     def launch_count(self):
@@ -125,6 +156,8 @@ class RDHandle:
     def resize_history(self, nt, dt):
         self._ck(self.lib.glia_rd_resize_history(self._h, int(nt), float(dt)))
         self.nt, self.dt = int(nt), float(dt)
+        if self.nranks > 1:
+            self._connect(1)
 
     def history_ptr(self, which, i):
         p = C.c_void_p()

@@ -43,6 +43,24 @@ const char* glia_rd_build_info(void);
  * context time step exactly like params->tu_->dt_ does in the DiffusionSolver ctor
  * (src/pde/DiffusionSolver.cpp:11); pass 0.5 for the reference default. */
 int glia_rd_create(glia_rd_t** h, const int n[3], int precision, int device, double dt_ctx);
+/* Slab-decomposed handle: one process per GPU, the grid cut along x into `nranks` (1, 2, 4 or
+ * 8) slabs, rank r owning x-planes [r*n0/nranks, (r+1)*n0/nranks) -- the local block AccFFT
+ * hands each rank for c_dims = {nranks, 1} (accfftCreateComm / accfft_local_size_dft_r2c,
+ * src/grad/SpectralOperators.cpp:24, 398-421; Grid::isize/istart, include/Parameters.h:374-451).
+ * `n` stays the GLOBAL grid; every field pointer passed to a slab handle is that rank's local
+ * block [n0/nranks][n1][n2].  Where the reference exchanges data with MPI all-to-all inside
+ * every FFT, the ranks here map each other's field arenas (CUDA IPC over NVLink) and the
+ * x-axis sweeps read / write the owners' memory directly.  Set-up is collective:
+ *     create_slab  ->  ipc_export(0)  ->  [all-gather the 64-byte handles]  ->  ipc_connect(0)
+ * and again with which = 1 after every glia_rd_resize_history.  Afterwards every call below
+ * is collective over the ranks (same calls, same order), like the MPI reference. */
+int glia_rd_create_slab(glia_rd_t** h, const int n[3], int precision, int device, double dt_ctx, int rank,
+                        int nranks);
+#define GLIA_IPC_HANDLE_BYTES 64
+/* which: 0 = work arena (after create), 1 = time-history arena (after resize_history) */
+int glia_rd_ipc_export(glia_rd_t* h, int which, void* handle64);
+/* handles: nranks * 64 bytes in rank order (the all-gathered exports) */
+int glia_rd_ipc_connect(glia_rd_t* h, int which, const void* handles);
 int glia_rd_destroy(glia_rd_t* h);
 const char* glia_rd_last_error(const glia_rd_t* h);
 /* the CUDA stream (cudaStream_t) all work of this handle is enqueued on */

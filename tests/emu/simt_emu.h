@@ -5,6 +5,10 @@
 // after another.  It is never loaded by the glia_b200 package.
 #pragma once
 #include <atomic>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <barrier>
 #include <functional>
 #include <memory>
@@ -133,6 +137,35 @@ inline int zero(void* d, size_t n, cudaStream_t) { std::memset(d, 0, n); return 
 inline int sync(cudaStream_t) { return 0; }
 inline int set_device(int) { return 0; }
 inline bool is_pinned(const void*) { return true; }
+// "IPC" of the emulator: POSIX shared memory, so that two emulator PROCESSES (the gloo
+// world_size-2 CPU tests) can map each other's arenas exactly like two GPU ranks do.
+inline int ipc_alloc(void** p, size_t n, unsigned char handle[64]) {
+  static int counter = 0;
+  std::memset(handle, 0, 64);
+  std::snprintf((char*)handle, 64, "/glia_emu_%d_%d", (int)getpid(), counter++);
+  int fd = shm_open((const char*)handle, O_CREAT | O_RDWR, 0600);
+  if (fd < 0) return 1;
+  if (ftruncate(fd, (off_t)n) != 0) { close(fd); return 1; }
+  void* m = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return 1;
+  *p = m;
+  return 0;
+}
+inline int ipc_open(void** p, const unsigned char handle[64], size_t n) {
+  int fd = shm_open((const char*)handle, O_RDWR, 0600);
+  if (fd < 0) return 1;
+  void* m = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return 1;
+  *p = m;
+  return 0;
+}
+inline void ipc_close(void* p, size_t n) { if (p) munmap(p, n); }
+inline void ipc_free(void* p, size_t n, const unsigned char* handle) {
+  if (p) munmap(p, n);
+  if (handle && handle[0]) shm_unlink((const char*)handle);
+}
 inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
 inline void stream_destroy(cudaStream_t) {}
 inline const char* err_string(int) { return "emu"; }
