@@ -47,16 +47,31 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256)
-    ap.add_argument("--nt", type=int, default=25)
-    ap.add_argument("--dt", type=float, default=0.04)
+    ap.add_argument("--workload", default="auto", choices=["auto", "rd256", "rd512", "slab512", "replicas"],
+                    help="auto: 1 GPU -> rd256 (BASELINE config[1]); N GPUs -> slab512 (config[3]: one 512^3 grid "
+                         "cut into N x-slabs, strong scaling). rd512 = the same 512^3 solve on one GPU (the strong-"
+                         "scaling base). replicas = N independent rd256 solves (weak).")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--nt", type=int, default=None)
+    ap.add_argument("--dt", type=float, default=None)
     ap.add_argument("--rho", type=float, default=8.0)
     ap.add_argument("--kappa", type=float, default=0.01)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "auto":
+        a.workload = "rd256" if max(world, a.gpus) == 1 else "slab512"
+    big = a.workload in ("rd512", "slab512")
+    if a.n is None:
+        a.n = 512 if big else 256
+    if a.nt is None:
+        a.nt = 10 if big else 25      # config 4 uses nt = 10, config 2 nt = 25
+    if a.dt is None:
+        a.dt = 1.0 / a.nt
+    return a
 
 
 def workload_config(a, world):
@@ -66,16 +81,32 @@ def workload_config(a, world):
         "n": a.n, "nt": a.nt, "dt": a.dt, "rho": a.rho, "kappa": a.kappa, "r_gm": 0.0, "k_gm": 0.0,
         "time_steps_per_bench_step": a.nt,
         "histories": "c_, c_half_, p_ stored (adjoint_store=1)",
-        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
-        "l2": "working set (time histories, >= 5 GB at 256^3) exceeds the 126 MB L2; no flush needed",
+        "parallelism": ("single GPU" if world == 1 else
+                        (f"one grid cut into {world} x-slabs (one per GPU); x sweeps on peer memory over NVLink"
+                         if a.workload == "slab512" else f"{world} independent replicas (one per GPU)")),
+        "l2": "working set (time histories, GBs per GPU) exceeds the 126 MB L2; no flush needed",
     }
 
 
 def make_inputs(a):
     from glia_b200 import synthetic as S
     dtype = np.float32 if a.precision == "f32" else np.float64
+    # the 512^3 generator costs about a minute of host FFTs: keep its output for the next run on this box
+    cache = os.path.join("/tmp", f"glia_b200_synth_{a.n}_{a.precision}_seed0.npz") if a.n >= 512 else None
+    if cache and os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            return {k: z[k] for k in ("wm", "gm", "csf", "vt", "filter")}, z["c0"], dtype
+        except Exception:
+            pass
     atlas = S.make_atlas(a.n, seed=0, dtype=dtype)
     c0 = S.make_initial_condition(atlas, seed=0, dtype=dtype)
+    if cache:
+        try:
+            np.savez(cache + ".tmp.npz", c0=c0, **atlas)
+            os.replace(cache + ".tmp.npz", cache)
+        except Exception:
+            pass
     return atlas, c0, dtype
 
 
@@ -138,7 +169,13 @@ ALG_F = {
     "kz_r2c": 2, "kz_r2c.axpy": 4, "ks_c2c.y": 2, "ks_pc": 2, "kz_c2r.rz": 3, "kz_c2r": 2, "kz_c2r.norm": 1,
     "k_cg_update": 5, "k_reaction": 4, "k_reaction_lin": 4, "k_axpby": 3,
     "k_pcg_alpha": 0, "k_pcg_beta": 0, "k_pcg_init": 0,
+    # slab-decomposed order: x sweep first (peer rows), z adds, y carries the epilogue
+    "kx_deriv2_dist": 3, "kz_deriv2.add": 4, "ks_deriv2.y.matvec": 4, "ks_deriv2.y.rhs": 5, "ks_deriv2.y.epi": 4,
+    "kx_pc_dist": 2, "k_peer_barrier": 0,
 }
+# fraction of a kernel's algorithmic bytes that crosses NVLink in slab mode is (G-1)/G of these (in F units)
+NVLINK_F = {"kx_deriv2_dist": 2, "kx_pc_dist": 2}
+NVLINK_PEAK_GBS = 900.0  # per direction per GPU (NVLink 5), B200_PROFILING.md
 
 
 def step_bytes_model(F, its_per_solve_total, nsolves, nt):
@@ -370,10 +407,173 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------- slab-decomposed arm ----
+def run_slab(a):
+    """One 512^3 (or --n) grid cut into WORLD_SIZE x-slabs, one rank per GPU (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from glia_b200.rd import RDHandle
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("--workload slab512 needs torchrun with >= 2 ranks (use --workload rd512 on one GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    gloo = dist.new_group(backend="gloo")  # carries the 64-byte IPC handles (host objects)
+
+    def all_gather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b, group=gloo)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dtype = np.float32 if a.precision == "f32" else np.float64
+    tdt = torch.float32 if a.precision == "f32" else torch.float64
+    lsh = (a.n // world, a.n, a.n)
+    F = float(np.dtype(dtype).itemsize) * a.n ** 3          # one GLOBAL field
+    Fl = F / world                                          # this rank's share
+    # rank 0 generates the global synthetic atlas and scatters the slabs
+    meta = [None]
+    fields = {}
+    if rank == 0:
+        atlas, c0, _ = make_inputs(a)
+        meta[0] = float(atlas["filter"].astype(np.float64).sum())
+        src = {"wm": atlas["wm"], "gm": atlas["gm"], "csf": atlas["csf"], "c0": c0}
+    dist.broadcast_object_list(meta, src=0, group=gloo)
+    fsum = meta[0]
+    for key in ("wm", "gm", "csf", "c0"):
+        out = torch.empty(lsh, dtype=tdt, device=dev)
+        if rank == 0:
+            g = torch.from_numpy(src[key]).to(dev)
+            dist.scatter(out, [g[r * lsh[0]:(r + 1) * lsh[0]].contiguous() for r in range(world)], src=0)
+            del g
+        else:
+            dist.scatter(out, None, src=0)
+        fields[key] = out
+    wm, gm, csf, c0d = fields["wm"], fields["gm"], fields["csf"], fields["c0"]
+    cT, p0, d1 = torch.empty_like(c0d), torch.empty_like(c0d), torch.empty_like(c0d)
+    torch.cuda.synchronize()
+
+    h = RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt, rank=rank, nranks=world, all_gather=all_gather)
+    h.resize_history(a.nt, a.dt)
+    h.set_diffusion_tissue(wm, gm, csf, 0.025, 0.0, 0.0, fsum)
+    h.set_reaction_tissue(wm, gm, csf, 10.0, 0.0, 0.0)
+    h.prec_factor()
+    h.solve_state(c0d, d1, 0)
+    h.set_diffusion_tissue(wm, gm, csf, a.kappa, 0.0, 0.0, fsum)
+    h.set_reaction_tissue(wm, gm, csf, a.rho, 0.0, 0.0)
+    h.prec_factor()
+
+    for _ in range(a.warmup):
+        ks, ka = h.forward_adjoint(c0d, d1, cT, p0)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = h.launch_count
+    h.timer_start()
+    for _ in range(a.steps):
+        ks, ka = h.forward_adjoint(c0d, d1, cT, p0)
+    ms = h.timer_stop_ms()
+    barrier()
+    launches = h.launch_count - l0
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    value = a.nt * a.steps / (ms * 1e-3)   # ONE job over all ranks: strong scaling
+
+    # ---- end to end: this rank's slabs from / to pinned host memory ---------------------------
+    hp = [torch.empty(lsh, dtype=tdt).pin_memory() for _ in range(4)]
+    hp[0].copy_(c0d.cpu())
+    hp[1].copy_(d1.cpu())
+    hn = [t.numpy() for t in hp]
+    h.forward_adjoint_host(hn[0], hn[1], hn[2], hn[3])
+    barrier()
+    h.timer_start()
+    for _ in range(a.steps):
+        h.forward_adjoint_host(hn[0], hn[1], hn[2], hn[3])
+    ms_e2e = h.timer_stop_ms()
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e_value = a.nt * a.steps / (ms_e2e * 1e-3)
+    e2e_ok = bool(np.array_equal(hn[2], cT.cpu().numpy()))
+
+    # ---- per-kernel profile of one more step (this rank's stream) -----------------------------
+    barrier()
+    h.profile_begin()
+    h.forward_adjoint(c0d, d1, cT, p0)
+    prof = h.profile_end()
+    barrier()
+    peak, peak_src = peaks()
+    kern = {}
+    tot_ms = sum(v[1] for v in prof.values())
+    for tag, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        avg = tms / cnt
+        fb = ALG_F.get(tag)
+        ach = (fb * Fl / (avg * 1e-3) / 1e9) if fb else None
+        k = {"launches": cnt, "avg_us": 1e3 * avg, "share": tms / tot_ms,
+             "alg_bytes_per_launch": fb * Fl if fb is not None else None,
+             "achieved_GBs": ach, "frac": (ach / peak) if ach else None}
+        if tag in NVLINK_F:
+            nvb = NVLINK_F[tag] * Fl * (world - 1) / world / 2.0     # per direction: half read, half written
+            k["nvlink_bytes_per_direction"] = nvb
+            k["nvlink_GBs_per_direction"] = nvb / (avg * 1e-3) / 1e9
+            k["nvlink_frac"] = k["nvlink_GBs_per_direction"] / NVLINK_PEAK_GBS
+        kern[tag] = k
+    dom = next(t for t in kern if kern[t]["achieved_GBs"] is not None)
+    nsolves = 4 * a.nt
+    model_bytes = step_bytes_model(Fl, ks + ka, nsolves, a.nt)          # per GPU
+    step_s = ms * 1e-3 / a.steps
+    step_ach = model_bytes / step_s / 1e9
+    nv_bytes = (world - 1) / world ** 2 * F * (6.0 * nsolves + 4.0 * (ks + ka)) / 2.0   # per direction per GPU
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
+        "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
+        "alg_bytes_per_launch": kern[dom]["alg_bytes_per_launch"], "avg_launch_us": kern[dom]["avg_us"],
+        "share_of_step": kern[dom]["share"],
+        "whole_step": {"alg_bytes_per_gpu": model_bytes, "achieved": step_ach, "frac": step_ach / peak,
+                       "model": "per GPU: (F/G)*[sum_solves(33+30*m_i)+10*nt] (SURVEY 8d A_min)"},
+        "nvlink": {"bytes_per_direction_per_gpu": nv_bytes, "achieved": nv_bytes / step_s / 1e9,
+                   "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": nv_bytes / step_s / 1e9 / NVLINK_PEAK_GBS,
+                   "model": "(G-1)/G^2 * F * [sum_solves(6 + 4 m_i)] split evenly over the two directions "
+                            "(SURVEY 8e); averaged over the whole step, the x sweeps alone are kernels[kx_*]"},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world),
+        "pcg_iterations": {"state": ks, "adjoint": ka, "solves": nsolves, "mean_per_solve": (ks + ka) / nsolves},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * F), "d2h_bytes_per_step": int(2 * F),
+                "ms_per_step": ms_e2e / a.steps, "matches_device_path": e2e_ok},
+        "gpu_launches": int(launches) * world,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kern,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "slab512":
+        run_slab(a)
     else:
         run_b200(a)
 

@@ -12,6 +12,7 @@
 #include "pointwise.cuh"
 #include "sweeps.cuh"
 #include "sweeps_dist.cuh"
+#include "sweeps_pipe.cuh"
 
 namespace glia {
 
@@ -47,6 +48,11 @@ inline int ipc_open(void** p, const unsigned char handle[64], size_t) {
 }
 inline void ipc_close(void* p, size_t) { if (p) cudaIpcCloseMemHandle(p); }
 inline void ipc_free(void* p, size_t, const unsigned char*) { if (p) cudaFree(p); }
+inline int sm_count(int device) {
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+  return v;
+}
 inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
@@ -158,6 +164,8 @@ class Engine : public EngineBase {
   bool hist_connected = false;
   Comm comm;
   unsigned epoch = 0, rseq = 0;
+  int nsm = 148;         // SMs of this device: grid size of the persistent (pipelined) sweeps
+  bool use_pipe = true;  // GLIA_RD_PIPE=0 selects the one-tile-per-CTA kernels (A/B measurements)
 
   // coefficients (kT, ktilT: pencil copies for the distributed x sweeps)
   T *kf = nullptr, *ktil = nullptr, *rho = nullptr, *kT = nullptr, *ktilT = nullptr;
@@ -204,6 +212,8 @@ class Engine : public EngineBase {
     if (n0l < 1 || n1l < 1 || (long)n0l * n[1] < 2) throw EngineError{"grid too small for this many slabs"};
     GLIA_CHECK(rt::set_device(device));
     GLIA_CHECK(rt::stream_create(&st));
+    nsm = rt::sm_count(device);
+    if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
     timer.create();
     nreal = (long)n0l * n[1] * n[2];
     ncplx = nreal / 2;
@@ -374,6 +384,38 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------ sweeps ----
   // acc = Dz(k Dz x); acc += Dy(k Dy x); then the x sweep with epilogue EPI
+  static RowsS<T> rows_s(const TileS& g, const void* ptr) {
+    return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, g.nchunk};
+  }
+  template <int N> dim3 grid_pipe(int ntiles) const {
+    const int g = nsm * pipe_ctas<T, N>();
+    return dim3((unsigned)(ntiles < g ? ntiles : g));
+  }
+  // one S-geometry D(k D x) sweep on local rows; returns the number of partial-sum blocks
+  template <int EPI>
+  int sweep_deriv2_local(int nline, const char* tag, const TileS& g, const T* x, const T* kfield, T alpha, T* out1,
+                         T* out2, double* pp, const int* done) {
+    constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
+    int nblk = 0;
+    GLIA_DISPATCH_N(nline, {
+      if (use_pipe && pipe_fits<T, N>()) {
+        const int ntiles = g.nchunk * g.n_outer;
+        const dim3 gr = grid_pipe<N>(ntiles);
+        nblk = (int)gr.x;
+        L(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
+          ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2), (const C*)tw_for(nline, g),
+          alpha, pp, done);
+      } else {
+        nblk = (int)grid_s(g).x;
+        L(tag, ks_deriv2<T, N, EPI>, grid_s(g), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, g, (const C*)x,
+          (const C*)kfield, (const C*)acc, (const C*)tw_for(nline, g), alpha, (C*)out1, (C*)out2, pp, done);
+      }
+    });
+    return nblk;
+  }
+  // twiddle table of the axis a TileS sweeps along (y tiles step rows by n2c, x tiles by n1*n2c)
+  const C* tw_for(int, const TileS& g) const { return g.row_stride == (long)n2c ? tw[1] : tw[0]; }
+
   // slab-decomposed form: the x sweep runs first, straight on the owners' memory, between two
   // rank barriers; the z sweep adds to it and the y sweep carries the epilogue.
   template <int EPI>
@@ -383,17 +425,23 @@ class Engine : public EngineBase {
     const TileS ty = tile_y();
     const PeerRows<T> xr = rows(x), ar = rows(acc);
     barrier();
-    GLIA_DISPATCH_N(n[0], L("kx_deriv2_dist", kx_deriv2_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, xr,
-                                       (const C*)kpen, ar, (const C*)tw[0], done));
+    GLIA_DISPATCH_N(n[0], {
+      if (use_pipe && pipe_fits<T, N>()) {
+        const int ntiles = txd.nchunk * txd.n_outer;
+        const RowsX<T> rx{xr, txd}, ra{ar, txd};
+        L("kx_deriv2_dist", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, grid_pipe<N>(ntiles),
+          block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)const_cast<T*>(kpen), txd}, ra, ra, ra,
+          (const C*)tw[0], (T)0, (double*)nullptr, done);
+      } else {
+        L("kx_deriv2_dist", kx_deriv2_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, xr, (const C*)kpen, ar,
+          (const C*)tw[0], done);
+      }
+    });
     barrier();
     GLIA_DISPATCH_N(n[2], L("kz_deriv2.add", kz_deriv2<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                        lines_z(), x, kfield, acc, (const C*)tw[2], done));
     const char* ytag = EPI == EPI_MATVEC ? "ks_deriv2.y.matvec" : (EPI == EPI_RHS ? "ks_deriv2.y.rhs" : "ks_deriv2.y.epi");
-    constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
-    GLIA_DISPATCH_N(n[1], L(ytag, ks_deriv2<T, N, EPI>, grid_s(ty), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, ty,
-                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[1], alpha, (C*)out1,
-                                       (C*)out2, pp, done));
-    return (int)grid_s(ty).x;
+    return sweep_deriv2_local<EPI>(n[1], ytag, ty, x, kfield, alpha, out1, out2, pp, done);
   }
 
   template <int EPI>
@@ -402,15 +450,9 @@ class Engine : public EngineBase {
     GLIA_DISPATCH_N(n[2], L("kz_deriv2", kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                        lines_z(), x, kfield, acc, (const C*)tw[2], done));
     const TileS ty = tile_y(), tx = tile_x();
-    GLIA_DISPATCH_N(n[1], L("ks_deriv2.y", ks_deriv2<T, N, EPI_ADD>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
-                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[1], (T)0, (C*)acc,
-                                       (C*)nullptr, (double*)nullptr, done));
+    sweep_deriv2_local<EPI_ADD>(n[1], "ks_deriv2.y", ty, x, kfield, (T)0, acc, nullptr, nullptr, done);
     const char* xtag = EPI == EPI_MATVEC ? "ks_deriv2.x.matvec" : (EPI == EPI_RHS ? "ks_deriv2.x.rhs" : "ks_deriv2.x");
-    constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
-    GLIA_DISPATCH_N(n[0], L(xtag, ks_deriv2<T, N, EPI>, grid_s(tx), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, tx,
-                                       (const C*)x, (const C*)kfield, (const C*)acc, (const C*)tw[0], alpha, (C*)out1,
-                                       (C*)out2, pp, done));
-    return (int)grid_s(tx).x;
+    return sweep_deriv2_local<EPI>(n[0], xtag, tx, x, kfield, alpha, out1, out2, pp, done);
   }
 
   // z = M^-1 r with optional prologue r -= a w, optional store, partial {<z,z>,<r,z>}
@@ -431,12 +473,27 @@ class Engine : public EngineBase {
       const TileX txd = tile_xd();
       const PeerRows<T> sr = rows((const T*)shat);
       barrier();
-      GLIA_DISPATCH_N(n[0], L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr,
-                                         (const C*)tw[0], sym, n[1], done));
+      GLIA_DISPATCH_N(n[0], {
+        if (use_pipe && pipe_fits<T, N>()) {
+          const int ntiles = txd.nchunk * txd.n_outer;
+          L("kx_pc_dist", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+            RowsX<T>{sr, txd}, (const C*)tw[0], sym, n[1], done);
+        } else {
+          L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr, (const C*)tw[0], sym, n[1],
+            done);
+        }
+      });
       barrier();
     } else {
-      GLIA_DISPATCH_N(n[0], L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat,
-                                         (const C*)tw[0], sym, n[1], done));
+      GLIA_DISPATCH_N(n[0], {
+        if (use_pipe && pipe_fits<T, N>()) {
+          const int ntiles = tx.nchunk * tx.n_outer;
+          L("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+            rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
+        } else {
+          L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat, (const C*)tw[0], sym, n[1], done);
+        }
+      });
     }
     GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
