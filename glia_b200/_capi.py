@@ -48,6 +48,10 @@ SIGNATURES = {
     "glia_rd_solve_state": (_I, [_P, _P, _P, _I, C.POINTER(_I)]),
     "glia_rd_solve_adjoint": (_I, [_P, _P, _P, _I, _I, C.POINTER(_I)]),
     "glia_rd_grad_kappa_rho": (_I, [_P, _P, _P, _P, C.POINTER(_D)]),
+    "glia_rd_set_secondary_tissue": (_I, [_P, _P, _P, _P, _D, _D, _D]),
+    "glia_rd_objective_gradient": (_I, [_P, _P, _P, _P, _D, _P, _P, _P, C.POINTER(_D), _P, C.POINTER(_D),
+                                        C.POINTER(_I)]),
+    "glia_rd_hessian_matvec": (_I, [_P, _P, _P, _D, _I, _P, _P, _P, _P, C.POINTER(_D), C.POINTER(_I)]),
     "glia_rd_profile_begin": (_I, [_P]),
     "glia_rd_profile_end": (_I, [_P, C.c_char_p, _I]),
     "glia_rd_timer_start": (_I, [_P]),

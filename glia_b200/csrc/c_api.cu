@@ -168,6 +168,29 @@ int glia_rd_solve_adjoint(glia_rd_t* h, const void* pT, void* p0, int lin, int s
 int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double out[6]) {
   return guarded(h, [&](EngineBase& E) { E.v_grad_kappa_rho(wm, gm, csf, out); });
 }
+int glia_rd_set_secondary_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double k1, double k2,
+                                 double k3) {
+  return guarded(h, [&](EngineBase& E) { E.v_set_secondary_tissue(wm, gm, csf, k1, k2, k3); });
+}
+int glia_rd_objective_gradient(glia_rd_t* h, const void* c0, const void* d1, const void* obs, double beta,
+                               const void* wm, const void* gm, const void* csf, double J[3], void* g_c0, double g[6],
+                               int ksp_its[2]) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!c0 || !d1 || !J || !g) throw EngineError{"objective_gradient: null argument"};
+    int k[2] = {0, 0};
+    E.v_objective_gradient(c0, d1, obs, beta, wm, gm, csf, J, g_c0, g, k);
+    if (ksp_its) { ksp_its[0] = k[0]; ksp_its[1] = k[1]; }
+  });
+}
+int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, double beta, int diffusivity_inversion,
+                           const void* wm, const void* gm, const void* csf, void* y_c0, double hk[6], int ksp_its[4]) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!c0_tilde || !y_c0 || !hk) throw EngineError{"hessian_matvec: null argument"};
+    int k[4] = {0, 0, 0, 0};
+    E.v_hessian_matvec(c0_tilde, obs, beta, diffusivity_inversion, wm, gm, csf, y_c0, hk, k);
+    if (ksp_its) for (int i = 0; i < 4; ++i) ksp_its[i] = k[i];
+  });
+}
 int glia_rd_profile_begin(glia_rd_t* h) {
   return guarded(h, [&](EngineBase& E) { E.v_profile_begin(); });
 }

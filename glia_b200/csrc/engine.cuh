@@ -794,6 +794,75 @@ class Engine : public EngineBase {
     out[3] = leb * s[0]; out[4] = leb * s[1]; out[5] = leb * s[2];
   }
 
+  // ------------------------------------ objective / gradient / Hessian ----
+  // DiffCoef::setSecondaryCoefficients (src/mat/DiffCoef.cpp:44-59): k~ = k1 wm + k2 gm + k3 csf
+  void set_secondary_tissue(const T* wm, const T* gm, const T* csf, double k1, double k2, double k3) {
+    const dim3 g = grid_pw(nreal);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, ktil, (T)k1, wm, (T)0, (const T*)nullptr);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, ktil, (T)k2, gm, (T)1, (const T*)ktil);
+    L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, ktil, (T)k3, csf, (T)1, (const T*)ktil);
+    if (G > 1) build_pencil(ktil, ktilT);
+    sync();
+  }
+  // t = O c - d1, pT = -O^T t into Tr; returns { <t,t>, <c0,c0> } summed over all ranks
+  void terminal_condition(const T* c, const T* d1, const T* obs, const T* c0, double sums[2]) {
+    const dim3 g = grid_pw(nreal);
+    L("k_obs_mismatch", k_obs_mismatch<T>, g, dim3(256), 0, st, nreal, c, d1, obs, c0, Tr, part(0));
+    L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8, comm,
+      G > 1 ? next_epoch() : 0u, rseq++);
+    GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
+    sync();
+    sums[0] = h_out[0];
+    sums[1] = h_out[1];
+  }
+  double lebesgue() const { return (2.0 * M_PI / n[0]) * (2.0 * M_PI / n[1]) * (2.0 * M_PI / n[2]); }
+  // DerivativeOperatorsRD::evaluateObjectiveAndGradient in field space
+  // (src/grad/DerivativeOperatorsRD.cpp:130-226): J[3] = {J, mismatch term, regularisation},
+  // g_c0 = -h^3 (alpha(0) - beta c0)  (g_p = Phi^T g_c0), g[6] as grad_kappa_rho.
+  void objective_gradient(const T* c0, const T* d1, const T* obs, double beta, const T* wm, const T* gm, const T* csf,
+                          double J[3], T* g_c0, double g[6], int ksp[2]) {
+    const double leb = lebesgue();
+    ksp[0] = solve_state(c0, nullptr, 0);
+    double sums[2];
+    terminal_condition(c_t, d1, obs, c0, sums);
+    J[1] = leb * 0.5 * sums[0];
+    J[2] = 0.5 * beta * sums[1] * leb;
+    J[0] = J[1] + J[2];
+    ksp[1] = solve_adjoint(Tr, nullptr, 1, 1);
+    if (g_c0) {  // p0 - beta c0, then scaled by -h^3 (VecAXPY, VecScale)
+      L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, g_c0, (T)1, (const T*)p_0, (T)(-beta), c0);
+      L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, g_c0, (T)(-leb), (const T*)g_c0, (T)0,
+        (const T*)nullptr);
+    }
+    grad_kappa_rho(wm, gm, csf, g);
+  }
+  // DerivativeOperatorsRD::evaluateHessian in field space (src/grad/DerivativeOperatorsRD.cpp:229-438).
+  // y_c0 = h^3 (beta c0~ - alpha~(0)) [- h^3 alpha~_k(0)]; hk = h^3 <wm|gm|csf, T_kp>, <wm|gm|csf, T_kk>.
+  void hessian_matvec(const T* c0t, const T* obs, double beta, int diffusivity_inversion, const T* wm, const T* gm,
+                      const T* csf, T* y_c0, double hk[6], int ksp[4]) {
+    const double leb = lebesgue();
+    double sums[2], gtmp[6];
+    for (int i = 0; i < 6; ++i) hk[i] = 0;
+    for (int i = 0; i < 4; ++i) ksp[i] = 0;
+    ksp[0] = solve_state(c0t, nullptr, 1);
+    terminal_condition(c_t, nullptr, obs, nullptr, sums);
+    ksp[1] = solve_adjoint(Tr, nullptr, 2, 1);
+    // y = beta c0~ - p0 ; y *= h^3
+    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, y_c0, (T)beta, c0t, (T)-1, (const T*)p_0);
+    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, y_c0, (T)leb, (const T*)y_c0, (T)0, (const T*)nullptr);
+    if (!diffusivity_inversion) { sync(); return; }
+    grad_kappa_rho(wm, gm, csf, gtmp);
+    for (int i = 0; i < 3; ++i) hk[i] = gtmp[i];
+    GLIA_CHECK(rt::zero(Tr, sizeof(T) * nreal, st));
+    ksp[2] = solve_state(Tr, nullptr, 2);
+    terminal_condition(c_t, nullptr, obs, nullptr, sums);
+    ksp[3] = solve_adjoint(Tr, nullptr, 2, 1);
+    L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, y_c0, (T)(-leb), (const T*)p_0, (T)1, (const T*)y_c0);
+    grad_kappa_rho(wm, gm, csf, gtmp);
+    for (int i = 0; i < 3; ++i) hk[3 + i] = gtmp[i];
+    sync();
+  }
+
   // ------------------------------------------ forward + adjoint entries ----
   // solveState(0), p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:156-161), solveAdjoint(1)
   void forward_adjoint(const T* c0, const T* d1, T* cT, T* p0out, int* ks, int* ka) {
@@ -890,6 +959,18 @@ class Engine : public EngineBase {
   }
   void v_grad_kappa_rho(const void* wm, const void* gm, const void* csf, double out[6]) override {
     grad_kappa_rho((const T*)wm, (const T*)gm, (const T*)csf, out);
+  }
+  void v_set_secondary_tissue(const void* wm, const void* gm, const void* csf, double k1, double k2, double k3) override {
+    set_secondary_tissue((const T*)wm, (const T*)gm, (const T*)csf, k1, k2, k3);
+  }
+  void v_objective_gradient(const void* c0, const void* d1, const void* obs, double beta, const void* wm, const void* gm,
+                            const void* csf, double J[3], void* g_c0, double g[6], int ksp[2]) override {
+    objective_gradient((const T*)c0, (const T*)d1, (const T*)obs, beta, (const T*)wm, (const T*)gm, (const T*)csf, J,
+                       (T*)g_c0, g, ksp);
+  }
+  void v_hessian_matvec(const void* c0t, const void* obs, double beta, int dinv, const void* wm, const void* gm,
+                        const void* csf, void* y_c0, double hk[6], int ksp[4]) override {
+    hessian_matvec((const T*)c0t, (const T*)obs, beta, dinv, (const T*)wm, (const T*)gm, (const T*)csf, (T*)y_c0, hk, ksp);
   }
   void v_profile_begin() override { sync(); prof.begin(); }
   std::string v_profile_end() override { return prof.end(st); }

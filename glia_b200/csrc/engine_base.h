@@ -40,6 +40,11 @@ class EngineBase {
   virtual int v_solve_state(const void* c0, void* cT, int linearized) = 0;
   virtual int v_solve_adjoint(const void* pT, void* p0, int linearized, int adjoint_store) = 0;
   virtual void v_grad_kappa_rho(const void* wm, const void* gm, const void* csf, double out[6]) = 0;
+  virtual void v_set_secondary_tissue(const void* wm, const void* gm, const void* csf, double k1, double k2, double k3) = 0;
+  virtual void v_objective_gradient(const void* c0, const void* d1, const void* obs, double beta, const void* wm,
+                                    const void* gm, const void* csf, double J[3], void* g_c0, double g[6], int ksp[2]) = 0;
+  virtual void v_hessian_matvec(const void* c0t, const void* obs, double beta, int diffusivity_inversion, const void* wm,
+                                const void* gm, const void* csf, void* y_c0, double hk[6], int ksp[4]) = 0;
   virtual void v_profile_begin() = 0;
   virtual std::string v_profile_end() = 0;
   virtual void v_timer_start() = 0;

@@ -185,6 +185,41 @@ __global__ void k_axpby(long n, T* out, T a, const T* x, T b, const T* y) {
     out[i] = y ? a * x[i] + b * y[i] : a * x[i];
 }
 
+// mismatch and adjoint terminal condition of one objective evaluation
+// (src/grad/DerivativeOperatorsRD.cpp:24-29, 78-84; Obs::apply/applyT = mask product,
+// src/mat/Obs.cpp:75-140):   t = O c - d1 (d1 may be null) ;  pT = -(O t) ;
+// partial sums { <t,t>, <c0,c0> } (c0 may be null).
+template <typename T>
+__global__ void k_obs_mismatch(long n, const T* __restrict__ c, const T* __restrict__ d1, const T* __restrict__ obs,
+                               const T* __restrict__ c0, T* pT, double* partial) {
+  double acc[4] = {0, 0, 0, 0};
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    T t = c[i];
+    if (obs) t = t * obs[i];
+    if (d1) t = t - d1[i];
+    T q = t;
+    if (obs) q = q * obs[i];
+    pT[i] = q * (T)-1.0;
+    acc[0] += (double)t * (double)t;
+    if (c0) acc[1] += (double)c0[i] * (double)c0[i];
+  }
+  __shared__ double red[32 * 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  GLIA_UNROLL
+  for (int j = 0; j < 4; ++j) {
+    double v = acc[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid * 4 + j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double sum = 0;
+    for (int w = 0; w < nwarp; ++w) sum += red[w * 4 + threadIdx.x];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = sum;
+  }
+}
+
 // partial sums of up to 3 dot products <m_j, t> plus sum(t)
 template <typename T>
 __global__ void k_dot3(long n, const T* __restrict__ t, const T* __restrict__ m0, const T* __restrict__ m1,

@@ -34,7 +34,8 @@ inline std::unordered_map<const void*, size_t>& smem_attr_cache() {
 }
 template <class... KA, class... A>
 inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
-  if (smem > 48 * 1024) {
+  // opt in above 32 KB already: static __shared__ (reduction scratch) counts against the 48 KB default too
+  if (smem > 32 * 1024) {
     auto& m = smem_attr_cache();
     auto it = m.find((const void*)k);
     if (it == m.end() || it->second < smem) {

@@ -184,6 +184,25 @@ class RDHandle:
         self._ck(self.lib.glia_rd_grad_kappa_rho(self._h, _ptr(wm), _ptr(gm), _ptr(csf), out))
         return np.array(list(out))
 
+    def set_secondary_tissue(self, wm, gm, csf, k1, k2=0.0, k3=0.0):
+        self._ck(self.lib.glia_rd_set_secondary_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(k1), float(k2),
+                                                       float(k3)))
+
+    def objective_gradient(self, c0, d1, wm, gm, csf, obs=None, beta=0.0, g_c0=None):
+        """evaluateObjectiveAndGradient in field space -> dict(J, mismatch, reg, g6, its)."""
+        J, g, its = (C.c_double * 3)(), (C.c_double * 6)(), (C.c_int * 2)()
+        self._ck(self.lib.glia_rd_objective_gradient(self._h, _ptr(c0), _ptr(d1), _ptr(obs), float(beta), _ptr(wm),
+                                                     _ptr(gm), _ptr(csf), J, _ptr(g_c0), g, its))
+        return dict(J=J[0], mismatch=J[1], reg=J[2], g6=np.array(list(g)), its=(its[0], its[1]))
+
+    def hessian_matvec(self, c0_tilde, y_c0, wm, gm, csf, obs=None, beta=0.0, diffusivity_inversion=False):
+        """evaluateHessian in field space -> (hk[6], ksp_its[4]); y_c0 is filled."""
+        hk, its = (C.c_double * 6)(), (C.c_int * 4)()
+        self._ck(self.lib.glia_rd_hessian_matvec(self._h, _ptr(c0_tilde), _ptr(obs), float(beta),
+                                                 int(bool(diffusivity_inversion)), _ptr(wm), _ptr(gm), _ptr(csf),
+                                                 _ptr(y_c0), hk, its))
+        return np.array(list(hk)), list(its)
+
     # -- per-kernel profile -----------------------------------------------------------
     def profile_begin(self):
         self._ck(self.lib.glia_rd_profile_begin(self._h))

@@ -134,6 +134,34 @@ int glia_rd_solve_adjoint(glia_rd_t* h, const void* pT, void* p0, int linearized
  * evaluateHessian (DerivativeOperatorsRD.cpp:270-320, 355-407). */
 int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double out[6]);
 
+/* ---- L2b: DerivativeOperatorsRD drivers, in field space ------------------------------- */
+/* The Phi basis (src/mat/Phi.cpp) is outside this library: the initial condition c(0) = Phi p is
+ * an input field and the p-block of a gradient / Hessian product is returned as a field g with
+ * g_p = Phi^T g.  `obs` is the observation mask of Obs::apply / applyT (src/mat/Obs.cpp:75-140;
+ * NULL means O = I); regularisation is the L2 form (DerivativeOperatorsRD.cpp:36-39). */
+/* DiffCoef::setSecondaryCoefficients (src/mat/DiffCoef.cpp:44-59): k~ = k1 wm + k2 gm + k3 csf
+ * (the caller resolves the nk == 1 ratios). */
+int glia_rd_set_secondary_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double k1, double k2,
+                                 double k3);
+/* evaluateObjectiveAndGradient (DerivativeOperatorsRD.cpp:130-226): solveState(0), mismatch,
+ * p_T = -O^T(O c(1) - d1), solveAdjoint(1), gradDiffusion + gradReaction.
+ *   J[3]   = { J, h^3/2 ||O c(1) - d1||^2, beta/2 h^3 ||c0||^2 }
+ *   g_c0   = -h^3 (alpha(0) - beta c0)          (device field, may be NULL)
+ *   g[6]   = as glia_rd_grad_kappa_rho;  ksp_its[2] = { state, adjoint } iteration totals. */
+int glia_rd_objective_gradient(glia_rd_t* h, const void* c0, const void* d1, const void* obs, double beta,
+                               const void* wm, const void* gm, const void* csf, double J[3], void* g_c0, double g[6],
+                               int ksp_its[2]);
+/* evaluateHessian (DerivativeOperatorsRD.cpp:229-438), Gauss-Newton product about the state of
+ * the last objective_gradient call.  c0_tilde = Phi p~.  diffusivity_inversion = 0: y_c0 =
+ * h^3 (beta c0~ - alpha~(0)) only.  Otherwise also the Hkp / Hpk / Hkk blocks with k~ from
+ * glia_rd_set_secondary[_tissue]:  y_c0 -= h^3 alpha~_k(0),
+ *   hk[0..2] = h^3 <wm|gm|csf, int grad c . grad alpha~ dt>      (Hkp p~)
+ *   hk[3..5] = the same integral after the k~ solves              (Hkk k~)
+ * including the reference's stale p_[nt] term.  ksp_its[4] = state(1), adjoint(2), state(2),
+ * adjoint(2) iteration totals. */
+int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, double beta, int diffusivity_inversion,
+                           const void* wm, const void* gm, const void* csf, void* y_c0, double hk[6], int ksp_its[4]);
+
 /* ---- per-kernel profile (CUDA events around every launch on the handle's stream) ---- */
 /* begin: start recording; end: stop, and write one "tag launches total_ms" line per kernel
  * family into buf (NUL-terminated, truncated to buflen).  Replaces the reference's

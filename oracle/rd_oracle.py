@@ -514,6 +514,82 @@ def grad_kappa_rho(pde: PdeOperatorsRD, wm, gm, csf):
                      leb * d(wm, Tr), leb * d(gm, Tr), leb * d(csf, Tr)])
 
 
+class DerivativeOperatorsRD:
+    """Field-space restatement of DerivativeOperatorsRD::{evaluateObjective,
+    evaluateObjectiveAndGradient, evaluateHessian}
+    (src/grad/DerivativeOperatorsRD.cpp:7-438) with the Phi basis factored out: the
+    initial condition c(0) (resp. c~(0) = Phi p~) is an input field and the p-block of the
+    gradient / Hessian product is returned as the field g with g_p = Phi^T g.
+    Obs::apply / applyT are pointwise products with the observation mask
+    (src/mat/Obs.cpp:75-140); obs = None is O = I.  L2 regularisation
+    (:36-39).  The kappa / rho blocks are the six scalars of grad_kappa_rho."""
+
+    def __init__(self, pde: PdeOperatorsRD, wm, gm, csf, obs=None, beta=0.0):
+        self.pde, self.wm, self.gm, self.csf = pde, wm, gm, csf
+        self.obs = obs
+        self.beta = float(beta)
+        n0, n1, n2 = pde.k.shape
+        self.leb = (2 * np.pi / n0) * (2 * np.pi / n1) * (2 * np.pi / n2)
+        self.dtype = pde.dtype
+
+    def _O(self, x):
+        return x if self.obs is None else (x * self.obs).astype(self.dtype)
+
+    def _terminal(self, cT, d1):
+        """temp = O c(1) - d1 ; p_t = -O^T temp   (:27, :81-84)."""
+        temp = self._O(cT)
+        if d1 is not None:
+            temp = (temp - d1).astype(self.dtype)
+        pT = (self._O(temp) * self.dtype.type(-1.0)).astype(self.dtype)
+        return temp, pT
+
+    def evaluate_objective_and_gradient(self, c0, d1):
+        """-> dict(J, mismatch, reg, cT, p0, g_c0, g6); J = h^3/2 ||O c(1) - d1||^2 + beta/2 h^3 ||c0||^2,
+        g_c0 = -h^3 (alpha(0) - beta c0), g6 = grad_kappa_rho (:130-226)."""
+        d = DiffusionSolver._dot
+        pde = self.pde
+        cT = pde.solve_state(c0, 0)
+        temp, pT = self._terminal(cT, d1)
+        m1 = d(temp, temp)
+        reg = 0.5 * self.beta * d(c0, c0) * self.leb
+        J = self.leb * 0.5 * m1 + reg
+        p0 = pde.solve_adjoint(pT, 1)
+        t = self.dtype.type
+        g_c0 = ((p0 - t(self.beta) * c0).astype(self.dtype) * t(-self.leb)).astype(self.dtype)
+        g6 = grad_kappa_rho(pde, self.wm, self.gm, self.csf)
+        return dict(J=J, mismatch=self.leb * 0.5 * m1, reg=reg, cT=cT, p0=p0, g_c0=g_c0, g6=g6,
+                    its=(pde.ksp_state, pde.ksp_adj))
+
+    def evaluate_hessian(self, c0_tilde, diffusivity_inversion=False):
+        """Gauss-Newton Hessian product (:229-438).  Needs the state history of a previous
+        evaluate_objective_and_gradient (c_, c_half_; p_[nt] is the stale gradient adjoint, trap
+        T4).  With diffusivity_inversion the secondary coefficients (k.set_secondary) carry
+        k~.  -> (y_c0 field, hk[6] = h^3 <wm|gm|csf, T_kp>, h^3 <wm|gm|csf, T_kk>)."""
+        pde = self.pde
+        t = self.dtype.type
+        d = DiffusionSolver._dot
+        its = []
+        cTt = pde.solve_state(c0_tilde, 1)
+        its.append(pde.ksp_state)
+        _, pT = self._terminal(cTt, None)
+        p0 = pde.solve_adjoint(pT, 2)
+        its.append(pde.ksp_adj)
+        y = ((t(self.beta) * c0_tilde - p0).astype(self.dtype) * t(self.leb)).astype(self.dtype)
+        hk = np.zeros(6)
+        if diffusivity_inversion:
+            Tk, _ = grad_integrals(pde)
+            hk[0:3] = [self.leb * d(m, Tk) for m in (self.wm, self.gm, self.csf)]
+            cTt = pde.solve_state(np.zeros_like(c0_tilde), 2)
+            its.append(pde.ksp_state)
+            _, pT = self._terminal(cTt, None)
+            p0 = pde.solve_adjoint(pT, 2)
+            its.append(pde.ksp_adj)
+            y = (y + t(-self.leb) * p0).astype(self.dtype)
+            Tk, _ = grad_integrals(pde)
+            hk[3:6] = [self.leb * d(m, Tk) for m in (self.wm, self.gm, self.csf)]
+        return y, hk, its
+
+
 # --------------------------------------------------------------------------
 # fixtures shared by tests / bench
 # --------------------------------------------------------------------------

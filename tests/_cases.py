@@ -247,3 +247,38 @@ def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_gr
         res["grad_vals"] = (g, g_ref)
     h.close()
     return res
+
+
+def case_objective_hessian(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
+    """evaluateObjectiveAndGradient + Gauss-Newton Hessian product (with diffusivity inversion,
+    nk = 2) through the C ABI vs the oracle's DerivativeOperatorsRD, observation mask on."""
+    sh = shape3(n)
+    P = make_problem(n, dtype)
+    pde = O.PdeOperatorsRD(P["k"], P["rho"], nt, dt, dt_ctx=dt)
+    obs = (P["wm"] > 0.2).astype(dtype)
+    D = O.DerivativeOperatorsRD(pde, P["wm"], P["gm"], P["csf"], obs=obs, beta=beta)
+    d1 = (0.7 * P["c0"]).astype(dtype)
+    ref = D.evaluate_objective_and_gradient(P["c0"], d1)
+    h, dev = setup_handle(B, P, n, dtype, nt, dt)
+    obs_d = B.put(obs)
+    gc0 = B.empty(sh, dtype)
+    out = h.objective_gradient(B.put(P["c0"]), B.put(d1), dev["wm"], dev["gm"], dev["csf"], obs=obs_d, beta=beta, g_c0=gc0)
+    res = {"J": abs(out["J"] - ref["J"]) / abs(ref["J"]), "its": (out["its"], ref["its"]),
+           "g_c0": rel(B.get(gc0), ref["g_c0"]),
+           "g6": float(np.max(np.abs(out["g6"] - ref["g6"]) / np.maximum(np.abs(ref["g6"]), 1e-300)))}
+    P["k"].set_secondary(0.3, 0.1, 0.0, P["wm"], P["gm"], P["csf"], nk=2)
+    h.set_secondary_tissue(dev["wm"], dev["gm"], dev["csf"], 0.3, 0.1, 0.0)
+    c0t = (0.5 * P["c0"] * P["wm"]).astype(dtype)
+    y_ref, hk_ref, its_ref = D.evaluate_hessian(c0t, True)
+    y = B.empty(sh, dtype)
+    hk, its = h.hessian_matvec(B.put(c0t), y, dev["wm"], dev["gm"], dev["csf"], obs=obs_d, beta=beta,
+                               diffusivity_inversion=True)
+    res["h_its"] = (list(its), list(its_ref))
+    res["h_y"] = rel(B.get(y), y_ref)
+    res["h_k"] = float(np.max(np.abs(hk - hk_ref) / np.maximum(np.abs(hk_ref), 1e-300)))
+    # p-only Hessian (no diffusivity inversion)
+    y2_ref, _, _ = D.evaluate_hessian(c0t, False)
+    h.hessian_matvec(B.put(c0t), y, dev["wm"], dev["gm"], dev["csf"], obs=obs_d, beta=beta, diffusivity_inversion=False)
+    res["h_y_ponly"] = rel(B.get(y), y2_ref)
+    h.close()
+    return res

@@ -50,3 +50,12 @@ def test_forward_adjoint_gradient(B, dtype):
     tol = Cs.TOL[np.dtype(dtype)]
     assert r["cT"] < tol and r["p0"] < tol
     assert r["grad"] < 10 * tol, r["grad_vals"]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_objective_gradient_hessian(B, dtype):
+    r = Cs.case_objective_hessian(B, 32, dtype, nt=2)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["its"][0] == r["its"][1] and r["h_its"][0] == r["h_its"][1], r
+    assert r["J"] < 10 * tol and r["g_c0"] < 10 * tol and r["g6"] < 20 * tol, r
+    assert r["h_y"] < 10 * tol and r["h_y_ponly"] < 10 * tol and r["h_k"] < 50 * tol, r

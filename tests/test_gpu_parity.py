@@ -75,6 +75,18 @@ def test_forward_adjoint_gradient(B, n, nt, dtype):
     assert r["grad"] < 10 * tol, r["grad_vals"]
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n,nt", [(64, 4), (128, 2)])
+def test_objective_gradient_hessian(B, n, nt, dtype):
+    """config 3 of BASELINE.json in miniature: one evaluateObjectiveAndGradient and Gauss-Newton
+    Hessian products (incremental forward / adjoint, diffusivity inversion on and off)."""
+    r = Cs.case_objective_hessian(B, n, dtype, nt=nt)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["its"][0] == r["its"][1] and r["h_its"][0] == r["h_its"][1], r
+    assert r["J"] < 10 * tol and r["g_c0"] < 10 * tol and r["g6"] < 20 * tol, r
+    assert r["h_y"] < 10 * tol and r["h_y_ponly"] < 10 * tol and r["h_k"] < 50 * tol, r
+
+
 def test_adjoint_without_store(B):
     r = Cs.case_forward_adjoint(B, 64, np.float64, nt=2, dt=0.04, adjoint_store=False, with_grad=False)
     assert r["its_adj"][0] == r["its_adj"][1]
