@@ -191,6 +191,12 @@ int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, 
     if (ksp_its) for (int i = 0; i < 4; ++i) ksp_its[i] = k[i];
   });
 }
+int glia_rd_probe_xsweep(glia_rd_t* h, int what, int local_mask, int reps, double* ms_per_sweep) {
+  return guarded(h, [&](EngineBase& E) {
+    const double t = E.v_probe(what, local_mask, reps);
+    if (ms_per_sweep) *ms_per_sweep = t;
+  });
+}
 int glia_rd_profile_begin(glia_rd_t* h) {
   return guarded(h, [&](EngineBase& E) { E.v_profile_begin(); });
 }

@@ -166,6 +166,10 @@ class Engine : public EngineBase {
   unsigned epoch = 0, rseq = 0;
   int nsm = 148;         // SMs of this device: grid size of the persistent (pipelined) sweeps
   bool use_pipe = true;  // GLIA_RD_PIPE=0 selects the one-tile-per-CTA kernels (A/B measurements)
+  int z_minb = 1;        // resident CTAs per SM the z second-derivative sweep is compiled for (GLIA_RD_ZMINB: 1, 3, 4).
+                         // Measured at 256^3 f32: 1 (123 registers, no cap) 49.6 us; 3 / 4 (80 / 64 registers) 82 us
+  int dist_debug = 0;    // GLIA_RD_DIST_DEBUG: timing experiments only (results are WRONG): 1 = x sweeps read
+                         // local rows instead of peer rows, 2 = write local rows instead of peer rows
 
   // coefficients (kT, ktilT: pencil copies for the distributed x sweeps)
   T *kf = nullptr, *ktil = nullptr, *rho = nullptr, *kT = nullptr, *ktilT = nullptr;
@@ -214,6 +218,8 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::stream_create(&st));
     nsm = rt::sm_count(device);
     if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
+    if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
     timer.create();
     nreal = (long)n0l * n[1] * n[2];
     ncplx = nreal / 2;
@@ -314,8 +320,12 @@ class Engine : public EngineBase {
     return hist_arena && (const char*)ptr >= hist_arena && (const char*)ptr < hist_arena + hist_bytes;
   }
   // the same field in every rank's arena (or history arena)
-  PeerRows<T> rows(const T* f) const {
+  PeerRows<T> rows(const T* f, int dbg_bit = 0) const {
     PeerRows<T> pr{};
+    if (dbg_bit && (dist_debug & dbg_bit)) {
+      for (int q = 0; q < G; ++q) pr.base[q] = reinterpret_cast<C*>(const_cast<T*>(f));
+      return pr;
+    }
     if (in_arena(f)) {
       if (!connected) throw EngineError{"slab handle is not connected (glia_rd_ipc_connect)"};
       const size_t off = (const char*)f - arena;
@@ -384,6 +394,23 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------ sweeps ----
   // acc = Dz(k Dz x); acc += Dy(k Dy x); then the x sweep with epilogue EPI
+  // z sweep of the D-apply: acc (+)= D_z(k D_z x)
+  template <int ADD>
+  void sweep_deriv2_z(const char* tag, const T* x, const T* kfield, const int* done) {
+    GLIA_DISPATCH_N(n[2], {
+      // register budget: 3-4 resident CTAs only pay for the 256-thread single-precision shapes
+      const bool small = sizeof(T) == 4 && N <= 256;
+      if (small && z_minb == 4)
+        L(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+          lines_z(), x, kfield, acc, (const C*)tw[2], done);
+      else if (small && z_minb == 3)
+        L(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+          lines_z(), x, kfield, acc, (const C*)tw[2], done);
+      else
+        L(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x, kfield, acc,
+          (const C*)tw[2], done);
+    });
+  }
   static RowsS<T> rows_s(const TileS& g, const void* ptr) {
     return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, g.nchunk};
   }
@@ -423,7 +450,7 @@ class Engine : public EngineBase {
     const T* kpen = (kfield == kf) ? kT : ktilT;
     const TileX txd = tile_xd();
     const TileS ty = tile_y();
-    const PeerRows<T> xr = rows(x), ar = rows(acc);
+    const PeerRows<T> xr = rows(x, 1), ar = rows(acc, 2);
     barrier();
     GLIA_DISPATCH_N(n[0], {
       if (use_pipe && pipe_fits<T, N>()) {
@@ -438,8 +465,7 @@ class Engine : public EngineBase {
       }
     });
     barrier();
-    GLIA_DISPATCH_N(n[2], L("kz_deriv2.add", kz_deriv2<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                       lines_z(), x, kfield, acc, (const C*)tw[2], done));
+    sweep_deriv2_z<1>("kz_deriv2.add", x, kfield, done);
     const char* ytag = EPI == EPI_MATVEC ? "ks_deriv2.y.matvec" : (EPI == EPI_RHS ? "ks_deriv2.y.rhs" : "ks_deriv2.y.epi");
     return sweep_deriv2_local<EPI>(n[1], ytag, ty, x, kfield, alpha, out1, out2, pp, done);
   }
@@ -447,8 +473,7 @@ class Engine : public EngineBase {
   template <int EPI>
   int dapply(const T* x, const T* kfield, T alpha, T* out1, T* out2, double* pp, const int* done) {
     if (G > 1) return dapply_dist<EPI>(x, kfield, alpha, out1, out2, pp, done);
-    GLIA_DISPATCH_N(n[2], L("kz_deriv2", kz_deriv2<T, N>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                       lines_z(), x, kfield, acc, (const C*)tw[2], done));
+    sweep_deriv2_z<0>("kz_deriv2", x, kfield, done);
     const TileS ty = tile_y(), tx = tile_x();
     sweep_deriv2_local<EPI_ADD>(n[1], "ks_deriv2.y", ty, x, kfield, (T)0, acc, nullptr, nullptr, done);
     const char* xtag = EPI == EPI_MATVEC ? "ks_deriv2.x.matvec" : (EPI == EPI_RHS ? "ks_deriv2.x.rhs" : "ks_deriv2.x");
@@ -471,13 +496,13 @@ class Engine : public EngineBase {
                                        (const C*)shat, shat, (const C*)tw[1], done));
     if (G > 1) {
       const TileX txd = tile_xd();
-      const PeerRows<T> sr = rows((const T*)shat);
+      const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
       barrier();
       GLIA_DISPATCH_N(n[0], {
         if (use_pipe && pipe_fits<T, N>()) {
           const int ntiles = txd.nchunk * txd.n_outer;
           L("kx_pc_dist", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            RowsX<T>{sr, txd}, (const C*)tw[0], sym, n[1], done);
+            RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], done);
         } else {
           L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr, (const C*)tw[0], sym, n[1],
             done);
@@ -489,7 +514,7 @@ class Engine : public EngineBase {
         if (use_pipe && pipe_fits<T, N>()) {
           const int ntiles = tx.nchunk * tx.n_outer;
           L("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
+            rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
         } else {
           L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat, (const C*)tw[0], sym, n[1], done);
         }
@@ -863,6 +888,42 @@ class Engine : public EngineBase {
     sync();
   }
 
+  // measurement probe (slab handles): `reps` back-to-back x sweeps of the preconditioner (what = 0)
+  // or of the D-apply (what = 1) on whatever the work buffers hold, with the peer reads and / or
+  // writes redirected to local memory by `local_mask` (1 = reads, 2 = writes).  Timing only.
+  double probe_xsweep(int what, int local_mask, int reps) {
+    if (G <= 1) throw EngineError{"probe_xsweep: slab handles only"};
+    const int saved = dist_debug;
+    dist_debug = local_mask;
+    const TileX txd = tile_xd();
+    const int ntiles = txd.nchunk * txd.n_outer;
+    GLIA_CHECK(rt::zero(shat, sizeof(T) * nreal, st));
+    GLIA_CHECK(rt::zero(p, sizeof(T) * nreal, st));
+    barrier();
+    sync();
+    timer.start(st);
+    for (int i = 0; i < reps; ++i) {
+      if (what == 0) {
+        const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
+        GLIA_DISPATCH_N(n[0], L("probe", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st,
+                                           ntiles, RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1],
+                                           (const int*)nullptr));
+      } else {
+        const PeerRows<T> xr = rows(p, 1), ar = rows(acc, 2);
+        const RowsX<T> rx{xr, txd}, ra{ar, txd};
+        GLIA_DISPATCH_N(n[0], L("probe", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>,
+                                           grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx,
+                                           RowsPen<T>{(C*)kT, txd}, ra, ra, ra, (const C*)tw[0], (T)0, (double*)nullptr,
+                                           (const int*)nullptr));
+      }
+    }
+    const double ms = timer.stop_ms(st);
+    barrier();
+    sync();
+    dist_debug = saved;
+    return ms / reps;
+  }
+
   // ------------------------------------------ forward + adjoint entries ----
   // solveState(0), p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:156-161), solveAdjoint(1)
   void forward_adjoint(const T* c0, const T* d1, T* cT, T* p0out, int* ks, int* ka) {
@@ -972,6 +1033,7 @@ class Engine : public EngineBase {
                         const void* csf, void* y_c0, double hk[6], int ksp[4]) override {
     hessian_matvec((const T*)c0t, (const T*)obs, beta, dinv, (const T*)wm, (const T*)gm, (const T*)csf, (T*)y_c0, hk, ksp);
   }
+  double v_probe(int what, int mask, int reps) override { return probe_xsweep(what, mask, reps); }
   void v_profile_begin() override { sync(); prof.begin(); }
   std::string v_profile_end() override { return prof.end(st); }
   void v_timer_start() override { timer.start(st); }

@@ -381,8 +381,8 @@ struct ZCtx {
 
 // Z-geometry second derivative: acc (+)= D_z(k D_z x)  (first sweep of applyD; ADD: second
 // sweep of the slab-decomposed applyD, whose x sweep runs first)
-template <typename T, int N, int ADD = 0>
-__global__ void __launch_bounds__(zthreads<N>())
+template <typename T, int N, int ADD = 0, int MINB = 1>
+__global__ void __launch_bounds__(zthreads<N>(), MINB)
 kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, const cplx<T>* __restrict__ twt,
           const int* __restrict__ done) {
   using F = LineFft<T, N>;

@@ -203,6 +203,11 @@ class RDHandle:
                                                  _ptr(y_c0), hk, its))
         return np.array(list(hk)), list(its)
 
+    def probe_xsweep(self, what, local_mask, reps=20):
+        ms = C.c_double(0)
+        self._ck(self.lib.glia_rd_probe_xsweep(self._h, int(what), int(local_mask), int(reps), C.byref(ms)))
+        return ms.value
+
     # -- per-kernel profile -----------------------------------------------------------
     def profile_begin(self):
         self._ck(self.lib.glia_rd_profile_begin(self._h))

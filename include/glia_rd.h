@@ -169,6 +169,11 @@ int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, 
 int glia_rd_profile_begin(glia_rd_t* h);
 int glia_rd_profile_end(glia_rd_t* h, char* buf, int buflen);
 
+/* measurement probe of the slab x sweeps (collective; the work buffers are overwritten):
+ * what 0 = preconditioner x sweep, 1 = D-apply x sweep; local_mask redirects the peer reads (1)
+ * and / or writes (2) to local memory, to separate NVLink pull, push and compute time. */
+int glia_rd_probe_xsweep(glia_rd_t* h, int what, int local_mask, int reps, double* ms_per_sweep);
+
 /* ---- timing helper (CUDA events on the handle's stream) --------------------------- */
 int glia_rd_timer_start(glia_rd_t* h);
 int glia_rd_timer_stop_ms(glia_rd_t* h, double* ms);
