@@ -527,7 +527,9 @@ def run_slab(a):
              "alg_bytes_per_launch": fb * Fl if fb is not None else None,
              "achieved_GBs": ach, "frac": (ach / peak) if ach else None}
         if tag in NVLINK_F:
-            nvb = NVLINK_F[tag] * Fl * (world - 1) / world / 2.0     # per direction: half read, half written
+            # an x sweep fetches (G-1)/G of its rows from peers and returns as many; every rank does
+            # both at once, so EACH direction of this GPU's links carries both amounts
+            nvb = NVLINK_F[tag] * Fl * (world - 1) / world
             k["nvlink_bytes_per_direction"] = nvb
             k["nvlink_GBs_per_direction"] = nvb / (avg * 1e-3) / 1e9
             k["nvlink_frac"] = k["nvlink_GBs_per_direction"] / NVLINK_PEAK_GBS
@@ -537,7 +539,7 @@ def run_slab(a):
     model_bytes = step_bytes_model(Fl, ks + ka, nsolves, a.nt)          # per GPU
     step_s = ms * 1e-3 / a.steps
     step_ach = model_bytes / step_s / 1e9
-    nv_bytes = (world - 1) / world ** 2 * F * (6.0 * nsolves + 4.0 * (ks + ka)) / 2.0   # per direction per GPU
+    nv_bytes = (world - 1) / world ** 2 * F * (6.0 * nsolves + 4.0 * (ks + ka))   # per direction per GPU
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
         "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom), "peak_source": peak_src,
@@ -547,8 +549,10 @@ def run_slab(a):
                        "model": "per GPU: (F/G)*[sum_solves(33+30*m_i)+10*nt] (SURVEY 8d A_min)"},
         "nvlink": {"bytes_per_direction_per_gpu": nv_bytes, "achieved": nv_bytes / step_s / 1e9,
                    "peak": NVLINK_PEAK_GBS, "unit": "GB/s", "frac": nv_bytes / step_s / 1e9 / NVLINK_PEAK_GBS,
-                   "model": "(G-1)/G^2 * F * [sum_solves(6 + 4 m_i)] split evenly over the two directions "
-                            "(SURVEY 8e); averaged over the whole step, the x sweeps alone are kernels[kx_*]"},
+                   "model": "per direction per GPU: (G-1)/G^2 * F * [sum_solves(6 + 4 m_i)] (SURVEY 8e: one exchange "
+                            "in and one out per x sweep); averaged over the whole step -- the x sweeps alone are "
+                            "kernels[kx_*].nvlink_frac; measured SM-issued peer copy rate on this box: ~740 GB/s "
+                            "pull, ~690 GB/s push (scripts/probes/p2p_probe.cu)"},
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -168,6 +168,7 @@ class Engine : public EngineBase {
   bool use_pipe = true;  // GLIA_RD_PIPE=0 selects the one-tile-per-CTA kernels (A/B measurements)
   int z_minb = 1;        // resident CTAs per SM the z second-derivative sweep is compiled for (GLIA_RD_ZMINB: 1, 3, 4).
                          // Measured at 256^3 f32: 1 (123 registers, no cap) 49.6 us; 3 / 4 (80 / 64 registers) 82 us
+  int z_minb512 = 1;     // the same for 512-point z lines (168 registers uncapped = 1 CTA/SM; 2 caps at 128)
   int dist_debug = 0;    // GLIA_RD_DIST_DEBUG: timing experiments only (results are WRONG): 1 = x sweeps read
                          // local rows instead of peer rows, 2 = write local rows instead of peer rows
 
@@ -220,6 +221,7 @@ class Engine : public EngineBase {
     if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
+    if (const char* e = std::getenv("GLIA_RD_ZMINB512")) z_minb512 = std::atoi(e);
     timer.create();
     nreal = (long)n0l * n[1] * n[2];
     ncplx = nreal / 2;
@@ -406,6 +408,9 @@ class Engine : public EngineBase {
       else if (small && z_minb == 3)
         L(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
           lines_z(), x, kfield, acc, (const C*)tw[2], done);
+      else if (sizeof(T) == 4 && (z_minb == 2 || (z_minb512 == 2 && N == 512)))
+        L(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x,
+          kfield, acc, (const C*)tw[2], done);
       else
         L(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x, kfield, acc,
           (const C*)tw[2], done);

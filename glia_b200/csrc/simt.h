@@ -36,6 +36,8 @@ template <class... KA, class... A>
 inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
   // opt in above 32 KB already: static __shared__ (reduction scratch) counts against the 48 KB default too
   if (smem > 32 * 1024) {
+    static std::mutex mu;  // handles on different host threads (ensemble members) launch concurrently
+    std::lock_guard<std::mutex> lock(mu);
     auto& m = smem_attr_cache();
     auto it = m.find((const void*)k);
     if (it == m.end() || it->second < smem) {

@@ -47,9 +47,30 @@ def _gauss_smooth(f, sigma):
     return sfft.irfftn(fh * g, s=n, workers=-1)
 
 
+def _upsample2(a):
+    """periodic linear interpolation to twice the resolution along every axis"""
+    for ax in range(a.ndim):
+        nxt = np.roll(a, -1, axis=ax)
+        out = np.empty(a.shape[:ax] + (2 * a.shape[ax],) + a.shape[ax + 1:], a.dtype)
+        idx = [slice(None)] * a.ndim
+        idx[ax] = slice(0, None, 2)
+        out[tuple(idx)] = a
+        idx[ax] = slice(1, None, 2)
+        out[tuple(idx)] = 0.5 * (a + nxt)
+        a = out
+    return a
+
+
 def make_atlas(n, seed=0, dtype=np.float32):
-    """-> dict(wm, gm, csf, vt, filter) of C-ordered [n0][n1][n2] arrays in `dtype`."""
+    """-> dict(wm, gm, csf, vt, filter) of C-ordered [n0][n1][n2] arrays in `dtype`.
+    Grids above 256^3 are the 256^3 atlas interpolated (periodic, linear) to the finer grid: the
+    same anatomy at every resolution, and no minute-long host FFTs before a multi-GPU run."""
     n = (n, n, n) if np.isscalar(n) else tuple(int(v) for v in n)
+    if min(n) > 256 and all(v % 2 == 0 for v in n):
+        coarse = make_atlas(tuple(v // 2 for v in n), seed, np.float32)
+        out = {k: np.ascontiguousarray(_upsample2(coarse[k]).astype(dtype)) for k in ("wm", "gm", "csf", "vt")}
+        out["filter"] = (((out["wm"] > 0.1) | (out["gm"] > 0.1)) & (out["vt"] < 0.8)).astype(dtype)
+        return out
     rng = np.random.default_rng(seed)
     ax = _axes(n)
     u = [(a - np.pi) / (2 * np.pi) for a in ax]  # box coordinates in [-0.5, 0.5)
@@ -90,9 +111,8 @@ def make_initial_condition(atlas, seed=0, n_gauss=3, dtype=np.float32):
         ctr = first if j == 0 else np.clip(first + rng.integers(-3, 4, 3) * np.maximum(np.array(n) // 64, 1),
                                            0, np.array(n) - 1)
         p = rng.uniform(0.5, 1.0)
-        r2 = ((ax[0] - ax[0][ctr[0]])[:, None, None] ** 2 + (ax[1] - ax[1][ctr[1]])[None, :, None] ** 2
-              + (ax[2] - ax[2][ctr[2]])[None, None, :] ** 2)
-        c0 += p * np.exp(-r2 / (2 * sig * sig))
+        g = [np.exp(-(ax[d] - ax[d][ctr[d]]) ** 2 / (2 * sig * sig)) for d in range(3)]  # separable Gaussian
+        c0 += p * (g[0][:, None, None] * g[1][None, :, None] * g[2][None, None, :])
     c0 *= atlas["filter"].astype(np.float64)
     c0 /= c0.max()
     return np.ascontiguousarray(c0.astype(dtype))

@@ -52,9 +52,9 @@ def test_forward_adjoint_gradient(B, dtype):
     assert r["grad"] < 10 * tol, r["grad_vals"]
 
 
-@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("dtype", [np.float64])   # single precision of the same case runs on the GPU
 def test_objective_gradient_hessian(B, dtype):
-    r = Cs.case_objective_hessian(B, 32, dtype, nt=2)
+    r = Cs.case_objective_hessian(B, 32, dtype, nt=1)
     tol = Cs.TOL[np.dtype(dtype)]
     assert r["its"][0] == r["its"][1] and r["h_its"][0] == r["h_its"][1], r
     assert r["J"] < 10 * tol and r["g_c0"] < 10 * tol and r["g6"] < 20 * tol, r

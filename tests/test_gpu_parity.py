@@ -239,3 +239,52 @@ def test_config1_brain_forward_adjoint_vs_golden(B, name, dtype):
     gr = z[f"{name}_grad"]
     assert np.max(np.abs(g - gr) / np.maximum(np.abs(gr), 1e-300)) < 20 * tol
     h.close()
+
+
+# ---- config 5 of BASELINE.json in miniature: independent ensemble members on one GPU ----------
+def test_ensemble_members_concurrent(B):
+    """inverse_ensemble-style batch: independent 128^3 forward solves with varied (kappa, rho), one
+    handle (= one stream) per member, driven concurrently from host threads.  Every member must
+    match the oracle and be bit-identical to the same member run alone."""
+    import threading
+    n, nt, dt, dtype = 128, 2, 0.04, np.float32
+    sh = (n, n, n)
+    P = Cs.make_problem(n, dtype)
+    params = [(0.005, 4.0), (0.02, 9.0), (0.05, 15.0), (0.01, 8.0)]
+    dev = {key: B.put(P[key]) for key in ("wm", "gm", "csf")}
+    fsum = float(P["filt"].sum(dtype=np.float64))
+    c0 = B.put(P["c0"])
+
+    def member(kappa, rho, out):
+        h = B.handle(n, dtype, dt_ctx=dt)
+        h.set_diffusion_tissue(dev["wm"], dev["gm"], dev["csf"], kappa, 0.2, 0.0, fsum)
+        h.set_reaction_tissue(dev["wm"], dev["gm"], dev["csf"], rho, 0.2, 0.0)
+        h.prec_factor()
+        h.resize_history(nt, dt)
+        its = h.solve_state(c0, out, 0)
+        h.close()
+        return its
+
+    alone = []
+    for kappa, rho in params:
+        o = B.empty(sh, dtype)
+        alone.append((member(kappa, rho, o), B.get(o)))
+    outs = [B.empty(sh, dtype) for _ in params]
+    its = [None] * len(params)
+
+    def run(i):
+        its[i] = member(params[i][0], params[i][1], outs[i])
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(params))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, (kappa, rho) in enumerate(params):
+        got = B.get(outs[i])
+        assert its[i] == alone[i][0]
+        assert np.array_equal(got, alone[i][1]), f"member {i} differs when run concurrently"
+        k = O.DiffCoef(sh, dtype)
+        k.set_values(kappa, 0.2, 0.0, P["wm"], P["gm"], P["csf"], P["filt"])
+        pde = O.PdeOperatorsRD(k, O.reac_coef(rho, 0.2, 0.0, P["wm"], P["gm"], P["csf"]), nt, dt, dt_ctx=dt)
+        ref = pde.solve_state(P["c0"], 0)
+        assert its[i] == pde.ksp_state, (i, its[i], pde.ksp_state)
+        assert Cs.rel(got, ref) < Cs.TOL[np.dtype(dtype)], (i, Cs.rel(got, ref))

@@ -9,7 +9,7 @@ import _cases as Cs
 import _slab
 
 
-@pytest.mark.parametrize("world,dtype", [(2, "float64"), (2, "float32"), (4, "float64")])
+@pytest.mark.parametrize("world,dtype", [(2, "float32"), (4, "float64")])
 def test_slab_operators(emu_lib, world, dtype):
     res = _slab.run(world, "emu", emu_lib, "operators", n=32, dtype=dtype)
     tol = 1e-12 if dtype == "float64" else 5e-6
@@ -18,7 +18,7 @@ def test_slab_operators(emu_lib, world, dtype):
         assert r["applyD"] <= max(r["applyD_budget"], tol), r
 
 
-@pytest.mark.parametrize("world,dtype", [(2, "float64"), (2, "float32")])
+@pytest.mark.parametrize("world,dtype", [(2, "float64")])   # float32 and worlds 2/4/8 run on the GPU box
 def test_slab_forward_adjoint_gradient(emu_lib, world, dtype):
     res = _slab.run(world, "emu", emu_lib, "forward_adjoint", n=32, dtype=dtype, nt=2)
     tol = Cs.TOL[np.dtype(dtype)]
