@@ -52,6 +52,11 @@ SIGNATURES = {
     "glia_rd_objective_gradient": (_I, [_P, _P, _P, _P, _D, _P, _P, _P, C.POINTER(_D), _P, C.POINTER(_D),
                                         C.POINTER(_I)]),
     "glia_rd_hessian_matvec": (_I, [_P, _P, _P, _D, _I, _P, _P, _P, _P, C.POINTER(_D), C.POINTER(_I)]),
+    "glia_rd_smooth": (_I, [_P, _P, _P, _D]),
+    "glia_rd_mat_prop": (_I, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(_D)]),
+    "glia_rd_phi_set": (_I, [_P, _I, C.POINTER(_D), _D, _P, _D]),
+    "glia_rd_phi_apply": (_I, [_P, _P, C.POINTER(_D)]),
+    "glia_rd_phi_apply_transpose": (_I, [_P, C.POINTER(_D), _P]),
     "glia_rd_probe_xsweep": (_I, [_P, _I, _I, _I, C.POINTER(_D)]),
     "glia_rd_profile_begin": (_I, [_P]),
     "glia_rd_profile_end": (_I, [_P, C.c_char_p, _I]),

@@ -191,6 +191,35 @@ int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, 
     if (ksp_its) for (int i = 0; i < 4; ++i) ksp_its[i] = k[i];
   });
 }
+int glia_rd_smooth(glia_rd_t* h, void* out, const void* in, double sigma) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!out || !in) throw EngineError{"smooth: null field"};
+    if (sigma < 0) throw EngineError{"smooth: negative sigma"};
+    E.v_smooth(out, in, sigma);
+  });
+}
+int glia_rd_mat_prop(glia_rd_t* h, void* gm, void* wm, void* vt, void* csf, void* bg, void* filter, double* filter_sum) {
+  return guarded(h, [&](EngineBase& E) {
+    const double s = E.v_mat_prop(gm, wm, vt, csf, bg, filter);
+    if (filter_sum) *filter_sum = s;
+  });
+}
+int glia_rd_phi_set(glia_rd_t* h, int np, const double* centers, double sigma_phi, const void* filter,
+                    double sigma_smooth) {
+  return guarded(h, [&](EngineBase& E) { E.v_phi_set(np, centers, sigma_phi, filter, sigma_smooth); });
+}
+int glia_rd_phi_apply(glia_rd_t* h, void* out, const double* p) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!out || !p) throw EngineError{"phi_apply: null argument"};
+    E.v_phi_apply(out, p);
+  });
+}
+int glia_rd_phi_apply_transpose(glia_rd_t* h, double* pout, const void* in) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!pout || !in) throw EngineError{"phi_apply_transpose: null argument"};
+    E.v_phi_apply_transpose(pout, in);
+  });
+}
 int glia_rd_probe_xsweep(glia_rd_t* h, int what, int local_mask, int reps, double* ms_per_sweep) {
   return guarded(h, [&](EngineBase& E) {
     const double t = E.v_probe(what, local_mask, reps);

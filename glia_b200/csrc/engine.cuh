@@ -10,6 +10,7 @@
 
 #include "engine_base.h"
 #include "pointwise.cuh"
+#include "phi.cuh"
 #include "sweeps.cuh"
 #include "sweeps_dist.cuh"
 #include "sweeps_pipe.cuh"
@@ -199,6 +200,17 @@ class Engine : public EngineBase {
   T *stage = nullptr, *TkX = nullptr;  // G > 1 only
   // host staging for the host-buffer entry point
   T *hs_in = nullptr, *hs_out = nullptr;
+  // Weierstrass smoother symbols (one real table per axis) and the Phi basis
+  T* symtab[3] = {nullptr, nullptr, nullptr};
+  double sym_sigma = -1.0;
+  T* phi_filter = nullptr;
+  bool phi_has_filter = false;
+  std::vector<double> phi_centers;
+  int phi_np = 0;
+  T phi_sigma = (T)0;
+  double phi_sigma_smooth = 0.0;
+  double* phi_dots = nullptr;
+  int phi_dots_cap = 0;
 
   int precision() const override { return (int)sizeof(T); }
 
@@ -279,6 +291,8 @@ class Engine : public EngineBase {
     rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal);
     rt::host_free(h_iscal); rt::host_free(h_out);
     rt::host_free(hs_in); rt::host_free(hs_out);
+    for (int a = 0; a < 3; ++a) rt::dev_free(symtab[a]);
+    rt::dev_free(phi_filter); rt::dev_free(phi_dots);
     timer.destroy();
     prof.destroy();
     rt::stream_destroy(st);
@@ -929,6 +943,178 @@ class Engine : public EngineBase {
     return ms / reps;
   }
 
+  // ------------------------------------------- smoother / Phi / MatProp ----
+  // symbol of the periodised, normalised Gaussian along every axis: s_d[k] = DFT(g_d)[k] / (sum(g_d) n_d),
+  // g_d(X) = exp(-X^2/2s^2) + exp(-(X-2pi)^2/2s^2)  (SpectralOperators.cpp:318-352 factorised).  The
+  // grid coordinates and sigma are rounded to ScalarType first, like the reference's loop does.
+  void build_symbol(double sigma) {
+    if (sigma == sym_sigma && symtab[0]) return;
+    const T twopi = (T)(2.0 * M_PI);
+    const T sg = (T)sigma;
+    for (int a = 0; a < 3; ++a) {
+      const int nn = n[a];
+      std::vector<double> g(nn);
+      std::vector<T> tab(nn);
+      if (sigma == 0.0) {  // identity (the reference returns early, SpectralOperators.cpp:272-274)
+        for (int k = 0; k < nn; ++k) tab[k] = (T)(1.0 / nn);
+      } else {
+        const T hh = twopi / (T)nn;
+        double S = 0;
+        for (int j = 0; j < nn; ++j) {
+          const T X = hh * (T)j;
+          const T Xp = X - twopi;
+          const double s2 = 2.0 * (double)sg * (double)sg;
+          g[j] = std::exp(-(double)X * (double)X / s2) + std::exp(-(double)Xp * (double)Xp / s2);
+          S += g[j];
+        }
+        for (int k = 0; k < nn; ++k) {
+          double re = 0;
+          for (int j = 0; j < nn; ++j) re += g[j] * std::cos(2.0 * M_PI * (double)((long)j * k % nn) / nn);
+          tab[k] = (T)(re / (S * nn));
+        }
+      }
+      if (!symtab[a]) GLIA_CHECK(rt::dev_malloc((void**)&symtab[a], sizeof(T) * nn));
+      GLIA_CHECK(rt::h2d(symtab[a], tab.data(), sizeof(T) * nn, st));
+      GLIA_CHECK(rt::sync(st));
+    }
+    sym_sigma = sigma;
+  }
+  void need_single(const char* what) const {
+    if (G > 1) throw EngineError{std::string(what) + ": single-GPU handles only (slab handles take c(0) as a field)"};
+  }
+  // SpectralOperators::weierstrassSmoother (src/grad/SpectralOperators.cpp:263-381); out may alias in
+  void smooth(T* out, const T* in, double sigma) {
+    need_single("glia_rd_smooth");
+    if (sigma == 0.0) {
+      if (out != in) GLIA_CHECK(rt::copy(out, in, sizeof(T) * nreal, st));
+      sync();
+      return;
+    }
+    build_symbol(sigma);
+    const TileS ty = tile_y(), tx = tile_x();
+    const GaussPhi<T> gp{};
+    GLIA_DISPATCH_N(n[2], L("kz_filter", kz_filter<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(),
+                                       in, out, (const T*)symtab[2], (const C*)tw[2], gp, n[1]));
+    GLIA_DISPATCH_N(n[1], L("ks_filter.y", ks_filter<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)out,
+                                       (C*)out, (const T*)symtab[1], (const C*)tw[1], gp, (C*)nullptr, (T)0,
+                                       (double*)nullptr, (double*)nullptr));
+    GLIA_DISPATCH_N(n[0], L("ks_filter.x", ks_filter<T, N, 0>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, (const C*)out,
+                                       (C*)out, (const T*)symtab[0], (const C*)tw[0], gp, (C*)nullptr, (T)0,
+                                       (double*)nullptr, (double*)nullptr));
+    sync();
+  }
+  // MatProp::setValuesCustom (src/mat/MatProp.cpp:135-201); returns sum(filter)
+  double mat_prop(T* gm, T* wm, T* vt, T* csf, T* bg, T* filter) {
+    const dim3 g = grid_pw(nreal);
+    L("k_mat_prop", k_mat_prop<T>, g, dim3(256), 0, st, nreal, gm, wm, vt, csf, bg, filter, part(0));
+    L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8, comm,
+      G > 1 ? next_epoch() : 0u, rseq++);
+    GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
+    sync();
+    return h_out[3];
+  }
+  // Phi::setGaussians / setValues (src/mat/Phi.cpp:24-120): centres, sigma, the MatProp filter
+  // (copied; null = no filter) and the smoothing width sigma_smooth = smoothing_factor 2pi/n0
+  void phi_set(int np, const double* centers, double sigma_phi, const T* filter, double sigma_smooth) {
+    need_single("glia_rd_phi_set");
+    if (np < 0 || (np > 0 && !centers)) throw EngineError{"phi_set: bad arguments"};
+    if (!(sigma_phi > 0)) throw EngineError{"phi_set: sigma must be positive"};
+    phi_np = np;
+    phi_centers.assign(centers, centers + 3 * (size_t)np);
+    phi_sigma = (T)sigma_phi;
+    phi_sigma_smooth = sigma_smooth;
+    phi_has_filter = filter != nullptr;
+    if (filter) {
+      if (!phi_filter) GLIA_CHECK(rt::dev_malloc((void**)&phi_filter, sizeof(T) * nreal));
+      GLIA_CHECK(rt::copy(phi_filter, filter, sizeof(T) * nreal, st));
+    }
+    if (np > phi_dots_cap) {
+      rt::dev_free(phi_dots);
+      phi_dots = nullptr;
+      GLIA_CHECK(rt::dev_malloc((void**)&phi_dots, sizeof(double) * np));
+      phi_dots_cap = np;
+    }
+    build_symbol(sigma_smooth);
+    sync();
+  }
+  GaussPhi<T> gauss(int i) const {
+    const T twopi = (T)(2.0 * M_PI);
+    GaussPhi<T> gp;
+    gp.xc = (T)phi_centers[3 * i]; gp.yc = (T)phi_centers[3 * i + 1]; gp.zc = (T)phi_centers[3 * i + 2];
+    gp.hx = twopi / (T)n[0]; gp.hy = twopi / (T)n[1]; gp.hz = twopi / (T)n[2];
+    gp.R = (T)(std::sqrt(2.) * (double)phi_sigma);
+    gp.sigma = phi_sigma;
+    return gp;
+  }
+  // basis function i into Tk up to (not including) the x sweep; returns the x-sweep grid size
+  void phi_zy(const GaussPhi<T>& gp) {
+    const TileS ty = tile_y();
+    GLIA_DISPATCH_N(n[2], L("kz_filter.gauss", kz_filter<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+                                       lines_z(), (const T*)(phi_has_filter ? phi_filter : nullptr), Tk,
+                                       (const T*)symtab[2], (const C*)tw[2], gp, n[1]));
+    GLIA_DISPATCH_N(n[1], L("ks_filter.y", ks_filter<T, N, 0>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)Tk,
+                                       (C*)Tk, (const T*)symtab[1], (const C*)tw[1], gp, (C*)nullptr, (T)0,
+                                       (double*)nullptr, (double*)nullptr));
+  }
+  // Phi::apply, on-the-fly mode (src/mat/Phi.cpp:324-383): out = sum_i p_i phi_i / max_i max(phi_i)
+  void phi_apply(T* out, const double* p) {
+    need_single("glia_rd_phi_apply");
+    if (phi_np <= 0) throw EngineError{"phi_apply: glia_rd_phi_set first"};
+    build_symbol(phi_sigma_smooth);
+    double* run_max = scal + 12;
+    GLIA_CHECK(rt::zero(out, sizeof(T) * nreal, st));
+    GLIA_CHECK(rt::zero(run_max, sizeof(double), st));
+    const TileS tx = tile_x();
+    const int nblk = (int)grid_s(tx).x;
+    bool nnz = false;
+    for (int i = 0; i < phi_np; ++i) {
+      const T pi = (T)p[i];
+      if (pi == (T)0) continue;  // adds nothing to sum_i phi_i p_i (Phi.cpp:343)
+      nnz = true;
+      const GaussPhi<T> gp = gauss(i);
+      phi_zy(gp);
+      GLIA_DISPATCH_N(n[0], L("ks_filter.x.phi", ks_filter<T, N, 1>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                         (const C*)Tk, (C*)Tk, (const T*)symtab[0], (const C*)tw[0], gp, (C*)out, pi, part(0),
+                                         (double*)nullptr));
+      L("k_phi_reduce", k_phi_reduce, dim3(1), dim3(256), 0, st, (const double*)part(0), (const double*)nullptr, nblk, run_max,
+        (double*)nullptr);
+    }
+    if (!nnz) {  // phi_max = 1 (Phi.cpp:377)
+      h_out[8] = 1.0;
+      GLIA_CHECK(rt::h2d(run_max, h_out + 8, sizeof(double), st));
+    }
+    L("k_scale_inv", k_scale_inv<T>, grid_pw(nreal), dim3(256), 0, st, nreal, out, (const double*)run_max);
+    sync();
+  }
+  // Phi::applyTranspose, on-the-fly mode (Phi.cpp:385-434): pout_i = <phi_i, in> / max_i max(phi_i)
+  void phi_apply_transpose(double* pout, const T* in) {
+    need_single("glia_rd_phi_apply_transpose");
+    if (phi_np <= 0) throw EngineError{"phi_apply_transpose: glia_rd_phi_set first"};
+    build_symbol(phi_sigma_smooth);
+    double* run_max = scal + 12;
+    GLIA_CHECK(rt::zero(run_max, sizeof(double), st));
+    const TileS tx = tile_x();
+    const int nblk = (int)grid_s(tx).x;
+    for (int i = 0; i < phi_np; ++i) {
+      const GaussPhi<T> gp = gauss(i);
+      phi_zy(gp);
+      GLIA_DISPATCH_N(n[0], L("ks_filter.x.phiT", ks_filter<T, N, 2>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx,
+                                         (const C*)Tk, (C*)Tk, (const T*)symtab[0], (const C*)tw[0], gp,
+                                         (C*)const_cast<T*>(in), (T)0, part(0), part(1)));
+      L("k_phi_reduce", k_phi_reduce, dim3(1), dim3(256), 0, st, (const double*)part(0), (const double*)part(1), nblk, run_max,
+        phi_dots + i);
+    }
+    std::vector<double> dots(phi_np + 1);
+    GLIA_CHECK(rt::d2h(h_out + 8, run_max, sizeof(double), st));
+    sync();
+    const T pm = (T)h_out[8];
+    // the dots come back through a pageable vector: small, once per call
+    GLIA_CHECK(rt::d2h(dots.data(), phi_dots, sizeof(double) * phi_np, st));
+    sync();
+    const T alpha = (T)(1.0 / (double)pm);
+    for (int i = 0; i < phi_np; ++i) pout[i] = (double)((T)dots[i] * alpha);
+  }
+
   // ------------------------------------------ forward + adjoint entries ----
   // solveState(0), p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:156-161), solveAdjoint(1)
   void forward_adjoint(const T* c0, const T* d1, T* cT, T* p0out, int* ks, int* ka) {
@@ -1038,6 +1224,15 @@ class Engine : public EngineBase {
                         const void* csf, void* y_c0, double hk[6], int ksp[4]) override {
     hessian_matvec((const T*)c0t, (const T*)obs, beta, dinv, (const T*)wm, (const T*)gm, (const T*)csf, (T*)y_c0, hk, ksp);
   }
+  void v_smooth(void* out, const void* in, double sigma) override { smooth((T*)out, (const T*)in, sigma); }
+  double v_mat_prop(void* gm, void* wm, void* vt, void* csf, void* bg, void* filter) override {
+    return mat_prop((T*)gm, (T*)wm, (T*)vt, (T*)csf, (T*)bg, (T*)filter);
+  }
+  void v_phi_set(int np, const double* centers, double sigma_phi, const void* filter, double sigma_smooth) override {
+    phi_set(np, centers, sigma_phi, (const T*)filter, sigma_smooth);
+  }
+  void v_phi_apply(void* out, const double* p) override { phi_apply((T*)out, p); }
+  void v_phi_apply_transpose(double* pout, const void* in) override { phi_apply_transpose(pout, (const T*)in); }
   double v_probe(int what, int mask, int reps) override { return probe_xsweep(what, mask, reps); }
   void v_profile_begin() override { sync(); prof.begin(); }
   std::string v_profile_end() override { return prof.end(st); }

@@ -45,6 +45,11 @@ class EngineBase {
                                     const void* gm, const void* csf, double J[3], void* g_c0, double g[6], int ksp[2]) = 0;
   virtual void v_hessian_matvec(const void* c0t, const void* obs, double beta, int diffusivity_inversion, const void* wm,
                                 const void* gm, const void* csf, void* y_c0, double hk[6], int ksp[4]) = 0;
+  virtual void v_smooth(void* out, const void* in, double sigma) = 0;
+  virtual double v_mat_prop(void* gm, void* wm, void* vt, void* csf, void* bg, void* filter) = 0;
+  virtual void v_phi_set(int np, const double* centers, double sigma_phi, const void* filter, double sigma_smooth) = 0;
+  virtual void v_phi_apply(void* out, const double* p) = 0;
+  virtual void v_phi_apply_transpose(double* pout, const void* in) = 0;
   virtual double v_probe(int what, int local_mask, int reps) = 0;
   virtual void v_profile_begin() = 0;
   virtual std::string v_profile_end() = 0;

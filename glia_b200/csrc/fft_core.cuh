@@ -32,6 +32,42 @@ __device__ __forceinline__ cplx<T> cmulc(cplx<T> a, cplx<T> b) {  // a * conj(b)
   return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
 }
 
+// ------------------------------------------------- L2 residency hints ----
+// At 256^3 single precision one field is 67 MB and B200's L2 holds 126 MB: of the fields a PCG
+// iteration touches, exactly one fits next to the streams.  The sweeps therefore read every
+// operand that is consumed once per kernel (x, k, r, w, the last read of acc / shat / z) with
+// the evict-first policy (ld.global.cs), so that the field handed from one kernel to the next
+// (acc -> w -> shat -> z -> p) survives in L2 until its consumer runs.  Measured with
+// scripts/probes/l2_probe.cu (profiles/r1b_l2_probe.txt): a 4F read-modify-write kernel whose
+// accumulator was left in L2 by its producer runs at 7.4-7.6 TB/s effective against 5.5 TB/s
+// unhinted; pinning with evict_last or a persisting window adds nothing over this.
+#ifndef GLIA_L2_HINTS
+#define GLIA_L2_HINTS 1
+#endif
+#if defined(GLIA_SIMT_EMU) || !GLIA_L2_HINTS
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return *p; }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { *p = v; }
+#else
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ cplx<float> ld_stream(const cplx<float>* p) {
+  const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+  return {v.x, v.y};
+}
+__device__ __forceinline__ cplx<double> ld_stream(const cplx<double>* p) {
+  const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(cplx<float>* p, cplx<float> v) {
+  __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+}
+__device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+#endif
+
 // ---------------------------------------------------------------- plans ----
 template <int N> struct FftPlan;
 template <> struct FftPlan<32>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 4,  R2 = 1; };

@@ -125,9 +125,10 @@ __global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const d
   const int done = iscal[I_DONE];
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // x and z are touched once per iteration (streamed); p stays in L2 for the next D-apply
     const T pv = p[i];
-    x[i] = x[i] + a * pv;
-    if (!done) p[i] = z[i] + b * pv;
+    st_stream(x + i, ld_stream(x + i) + a * pv);
+    if (!done) p[i] = ld_stream(z + i) + b * pv;
   }
 }
 

@@ -401,8 +401,8 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
     GLIA_UNROLL
     for (int a = 0; a < F::R(0); ++a) {
       const int pos = F::template loc<0>(z.t, g, a);
-      v[g * F::R(0) + a] = {x[la + pos], x[lb + pos]};
-      kk[g * F::R(0) + a] = {kf[la + pos], kf[lb + pos]};
+      v[g * F::R(0) + a] = {ld_stream(x + la + pos), ld_stream(x + lb + pos)};
+      kk[g * F::R(0) + a] = {ld_stream(kf + la + pos), ld_stream(kf + lb + pos)};
     }
   deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
   GLIA_UNROLL
@@ -555,11 +555,12 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
     GLIA_UNROLL
     for (int a = 0; a < F::R(0); ++a) {
       const int pos = F::template loc<0>(z.t, g, a);
-      cplx<T> rv = {r[la + pos], r[lb + pos]};
+      // r and w are streamed: neither is re-read before most of L2 has turned over
+      cplx<T> rv = {ld_stream(r + la + pos), ld_stream(r + lb + pos)};
       if (PRO) {
-        rv.x = rv.x - aa * w[la + pos];
-        rv.y = rv.y - aa * w[lb + pos];
-        if (z.active) { r[la + pos] = rv.x; r[lb + pos] = rv.y; }
+        rv.x = rv.x - aa * ld_stream(w + la + pos);
+        rv.y = rv.y - aa * ld_stream(w + lb + pos);
+        if (z.active) { st_stream(r + la + pos, rv.x); st_stream(r + lb + pos, rv.y); }
       }
       v[g * F::R(0) + a] = rv;
     }
@@ -617,7 +618,7 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
   GLIA_UNROLL
   for (int j = 0; j < E / 2; ++j) {
     const int k = z.t + F::TPL * j;
-    const cplx<T> A = shat[oa + k], B = shat[ob + k];
+    const cplx<T> A = ld_stream(shat + oa + k), B = ld_stream(shat + ob + k);  // last read of shat
     if (k == 0) {
       sm[am(F::loc_of_freq(0))] = {A.x, B.x};
       sm[am(F::loc_of_freq(N / 2))] = {A.y, B.y};
@@ -644,7 +645,7 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
         if (zout) { zout[la + pos] = zv.x; zout[lb + pos] = zv.y; }
         if (EPI) {
           acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
-          if (r) acc[1] += (double)r[la + pos] * (double)zv.x + (double)r[lb + pos] * (double)zv.y;
+          if (r) acc[1] += (double)ld_stream(r + la + pos) * (double)zv.x + (double)ld_stream(r + lb + pos) * (double)zv.y;
         }
       }
     }

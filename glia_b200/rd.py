@@ -208,6 +208,34 @@ class RDHandle:
         self._ck(self.lib.glia_rd_probe_xsweep(self._h, int(what), int(local_mask), int(reps), C.byref(ms)))
         return ms.value
 
+    # -- smoother / MatProp / Phi (callers either side of the path) ------------------------
+    def smooth(self, out, inp, sigma):
+        """SpectralOperators::weierstrassSmoother; ``out`` may alias ``inp``."""
+        self._ck(self.lib.glia_rd_smooth(self._h, _ptr(out), _ptr(inp), float(sigma)))
+
+    def mat_prop(self, gm, wm, vt, csf, bg=None, filt=None):
+        """MatProp::setValuesCustom: clips the maps in place, fills bg / filter; -> sum(filter)."""
+        s = C.c_double(0)
+        self._ck(self.lib.glia_rd_mat_prop(self._h, _ptr(gm), _ptr(wm), _ptr(vt), _ptr(csf), _ptr(bg), _ptr(filt),
+                                           C.byref(s)))
+        return s.value
+
+    def phi_set(self, centers, sigma_phi, filt=None, sigma_smooth=0.0):
+        ctr = np.ascontiguousarray(np.asarray(centers, dtype=np.float64).reshape(-1, 3))
+        self._phi_np = ctr.shape[0]
+        self._ck(self.lib.glia_rd_phi_set(self._h, self._phi_np, ctr.ctypes.data_as(C.POINTER(C.c_double)),
+                                          float(sigma_phi), _ptr(filt), float(sigma_smooth)))
+
+    def phi_apply(self, out, p):
+        pv = np.ascontiguousarray(np.asarray(p, dtype=np.float64).ravel())
+        assert pv.size == self._phi_np
+        self._ck(self.lib.glia_rd_phi_apply(self._h, _ptr(out), pv.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def phi_apply_transpose(self, inp):
+        out = np.zeros(self._phi_np, dtype=np.float64)
+        self._ck(self.lib.glia_rd_phi_apply_transpose(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), _ptr(inp)))
+        return out
+
     # -- per-kernel profile -----------------------------------------------------------
     def profile_begin(self):
         self._ck(self.lib.glia_rd_profile_begin(self._h))

@@ -162,6 +162,26 @@ int glia_rd_objective_gradient(glia_rd_t* h, const void* c0, const void* d1, con
 int glia_rd_hessian_matvec(glia_rd_t* h, const void* c0_tilde, const void* obs, double beta, int diffusivity_inversion,
                            const void* wm, const void* gm, const void* csf, void* y_c0, double hk[6], int ksp_its[4]);
 
+/* ---- callers either side of the path: smoother, MatProp, Phi (single-GPU handles) ---------- */
+/* SpectralOperators::weierstrassSmoother (src/grad/SpectralOperators.cpp:263-381): periodic
+ * Gaussian smoothing with width sigma; out may alias in; sigma == 0 copies. */
+int glia_rd_smooth(glia_rd_t* h, void* out, const void* in, double sigma);
+/* MatProp::setValuesCustom (src/mat/MatProp.cpp:135-201): clips gm / wm / vt / csf at 0 IN PLACE
+ * (null = absent map), bg = 1 - sum, filter = (wm > 0.1 || gm > 0.1) && vt < 0.8 (bg, filter may
+ * be null); *filter_sum = sum(filter), the divisor of DiffCoef's average coefficients. */
+int glia_rd_mat_prop(glia_rd_t* h, void* gm, void* wm, void* vt, void* csf, void* bg, void* filter,
+                     double* filter_sum);
+/* Phi::setGaussians / setValues (src/mat/Phi.cpp:24-120): np Gaussians with HOST centres
+ * centers[3*np] (radians) and width sigma_phi, the MatProp filter (device field, copied; null =
+ * none) and sigma_smooth = smoothing_factor * 2 pi / n0 (Phi.cpp:338). */
+int glia_rd_phi_set(glia_rd_t* h, int np, const double* centers, double sigma_phi, const void* filter,
+                    double sigma_smooth);
+/* Phi::apply in on-the-fly mode (Phi.cpp:324-383): out = sum_i p_i phi_i / max_i max(phi_i),
+ * phi_i = truncate_{5 sigma}(W(Gaussian_i . filter)); p is a HOST array of np values. */
+int glia_rd_phi_apply(glia_rd_t* h, void* out, const double* p);
+/* Phi::applyTranspose (Phi.cpp:385-434): pout_i = <phi_i, in> / max_i max(phi_i) (HOST, np). */
+int glia_rd_phi_apply_transpose(glia_rd_t* h, double* pout, const void* in);
+
 /* ---- per-kernel profile (CUDA events around every launch on the handle's stream) ---- */
 /* begin: start recording; end: stop, and write one "tag launches total_ms" line per kernel
  * family into buf (NUL-terminated, truncated to buflen).  Replaces the reference's

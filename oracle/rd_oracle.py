@@ -681,3 +681,44 @@ def phi_apply(p, centers, sigma_phi, filt, smoothing_factor=1.0):
     if not nnz:
         phi_max = t(1)
     return (out * (t(1.0) / phi_max)).astype(dt)
+
+
+def _phi_i(ctr, X, Y, Z, sig, R, filt, sigma_smooth):
+    """One basis function of the on-the-fly mode: truncate(W(Gaussian . filter)).
+    Phi::initialize (src/mat/Phi.cpp:262-320) + VecPointwiseMult(filter) + weierstrassSmoother +
+    Phi::truncate (Phi.cpp:237-260)."""
+    dt = filt.dtype
+    t = dt.type
+    dx = (X - t(ctr[0]))[:, None, None]
+    dy = (Y - t(ctr[1]))[None, :, None]
+    dz = (Z - t(ctr[2]))[None, None, :]
+    r = np.sqrt((dx * dx + dy * dy + dz * dz).astype(dt)).astype(dt)
+    ratio = (r / R).astype(dt)
+    phi = np.exp(-(ratio * ratio)).astype(dt)
+    phi = (filt * phi).astype(dt)
+    phi = weierstrass_smoother(phi, sigma_smooth)
+    return np.where((r / sig) <= 5, phi, 0).astype(dt)
+
+
+def phi_apply_transpose(field, centers, sigma_phi, filt, smoothing_factor=1.0):
+    """Phi::applyTranspose in on-the-fly mode (src/mat/Phi.cpp:385-434): pout_i = <phi_i, in>,
+    every i (no skipping), then pout *= 1 / max_i max(phi_i).  VecDot accumulates in the working
+    precision in PETSc; here it is accumulated in float64 and rounded once."""
+    dt = filt.dtype
+    t = dt.type
+    n0, n1, n2 = filt.shape
+    twopi = t(2.0 * np.pi)
+    hx, hy, hz = t(twopi / n0), t(twopi / n1), t(twopi / n2)
+    sigma_smooth = t(smoothing_factor * 2.0 * np.pi / n0)
+    sig = t(sigma_phi)
+    R = t(np.sqrt(2.0) * float(sig))
+    X = (hx * np.arange(n0).astype(dt)).astype(dt)
+    Y = (hy * np.arange(n1).astype(dt)).astype(dt)
+    Z = (hz * np.arange(n2).astype(dt)).astype(dt)
+    out = np.zeros(len(centers), dt)
+    phi_max = t(0)
+    for i, ctr in enumerate(centers):
+        phi = _phi_i(ctr, X, Y, Z, sig, R, filt, sigma_smooth)
+        phi_max = max(phi_max, t(phi.max()))
+        out[i] = t(np.sum(phi.astype(np.float64) * field.astype(np.float64)))
+    return (out * (t(1.0) / phi_max)).astype(dt)

@@ -282,3 +282,107 @@ def case_objective_hessian(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
     res["h_y_ponly"] = rel(B.get(y), y2_ref)
     h.close()
     return res
+
+
+# ------------------------------------------- smoother / MatProp / Phi ----
+def case_smooth(B, n, dtype, sigma_factor=1.0, seed=7):
+    """weierstrassSmoother through the C ABI (three 1-D symbol sweeps) vs the oracle's 3-D-FFT
+    restatement; also in place and sigma = 0."""
+    sh = shape3(n)
+    rng = np.random.default_rng(seed)
+    x = rng.random(sh).astype(dtype)
+    sigma = float(np.dtype(dtype).type(sigma_factor * 2 * np.pi / sh[0]))
+    ref = O.weierstrass_smoother(x.astype(np.float64), sigma)
+    h = B.handle(n, dtype)
+    xd, out = B.put(x), B.empty(sh, dtype)
+    h.smooth(out, xd, sigma)
+    e1 = rel(B.get(out), ref)
+    h.smooth(xd, xd, sigma)
+    e2 = rel(B.get(xd), ref)
+    xd = B.put(x)
+    h.smooth(out, xd, 0.0)
+    e0 = rel(B.get(out), x)
+    h.close()
+    return e1, e2, e0
+
+
+def case_mat_prop(B, n, dtype, seed=8):
+    sh = shape3(n)
+    rng = np.random.default_rng(seed)
+    maps = {k: (rng.random(sh) * 1.2 - 0.2).astype(dtype) for k in ("gm", "wm", "vt", "csf")}
+    maps["vt"] = (maps["vt"] * 1.0).astype(dtype)
+    ref = O.mat_prop(maps, sh, np.dtype(dtype).type)
+    h = B.handle(n, dtype)
+    dev = {k: B.put(v) for k, v in maps.items()}
+    bg, filt = B.empty(sh, dtype), B.empty(sh, dtype)
+    fs = h.mat_prop(dev["gm"], dev["wm"], dev["vt"], dev["csf"], bg, filt)
+    ok = all(np.array_equal(B.get(dev[k]), ref[k]) for k in ("gm", "wm", "vt", "csf"))
+    ok = ok and np.array_equal(B.get(filt), ref["filter"]) and np.array_equal(B.get(bg), ref["bg"])
+    # vt absent
+    gm2, wm2 = B.put(maps["gm"]), B.put(maps["wm"])
+    fs2 = h.mat_prop(gm2, wm2, None, None, None, filt)
+    ref2 = O.mat_prop({"gm": maps["gm"], "wm": maps["wm"]}, sh, np.dtype(dtype).type)
+    ok = ok and np.array_equal(B.get(filt), ref2["filter"]) and fs2 == float(ref2["filter"].sum(dtype=np.float64))
+    h.close()
+    return ok, fs, float(ref["filter"].sum(dtype=np.float64))
+
+
+def case_phi(B, n, dtype, sigma_factor=2.0):
+    """Phi::apply / applyTranspose (on-the-fly mode) through the C ABI vs the oracle, with a
+    filter, a zero coefficient (skipped basis function) and the all-zero p case."""
+    sh = shape3(n)
+    wm, gm, csf, filt = tissue(sh, dtype)
+    sig = 2 * np.pi / sh[0] * sigma_factor
+    ctr = [(3.0, 3.3, 2.8), (2.4, 3.0, 3.4), (3.6, 2.7, 3.0)]
+    p = [1.0, 0.0, 0.6]
+    ref = O.phi_apply(p, ctr, sig, filt, 1.0)
+    h = B.handle(n, dtype)
+    h.phi_set(ctr, sig, B.put(filt), 2 * np.pi / sh[0])
+    out = B.empty(sh, dtype)
+    h.phi_apply(out, p)
+    e_apply = rel(B.get(out), ref)
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal(sh).astype(dtype)
+    pt = h.phi_apply_transpose(B.put(f))
+    pt_ref = O.phi_apply_transpose(f, ctr, sig, filt, 1.0)
+    e_t = float(np.max(np.abs(pt - pt_ref) / np.max(np.abs(pt_ref))))
+    # adjointness <Phi p, f> = <p, Phi^T f> holds when every basis function takes part
+    p2 = [0.3, -0.8, 0.5]
+    h.phi_apply(out, p2)
+    lhs = float(np.sum(B.get(out).astype(np.float64) * f.astype(np.float64)))
+    rhs = float(np.dot(p2, pt))
+    e_adj = abs(lhs - rhs) / max(abs(lhs), 1e-300)
+    h.phi_apply(out, [0.0, 0.0, 0.0])
+    zero_ok = not np.any(B.get(out))
+    h.close()
+    return e_apply, e_t, e_adj, zero_ok
+
+
+def case_K2_K3(B, dtype, which):
+    """The reference's own pins for c(0) = Phi p (src/test/simulator.cpp:41-42, 94-95) computed by
+    the CUDA path end to end from the committed test data: smooth the tissue maps, MatProp filter,
+    Phi::apply.  -> (||c0||, expected, rel. error against the oracle's c0)."""
+    from golden import fixtures as FX
+    n = 64
+    t = np.dtype(dtype).type
+    h = B.handle(n, dtype)
+    sig_atlas = float(t(2 * np.pi / n))
+    if which == "K2":
+        maps = O.split_segmentation(FX.atlas_labels().astype(dtype), (6, 5, 7, 8), dtype)
+        dev = {k: B.put(maps[k]) for k in ("gm", "wm", "vt", "csf")}
+        for k in ("gm", "wm", "vt", "csf"):   # SolverInterface::readAtlas order
+            h.smooth(dev[k], dev[k], sig_atlas)
+        sigma_phi, expected = 2 * np.pi / 64, 4.09351
+        ref = FX.brain_problem(dtype)["c0"]
+    else:
+        dev = {"wm": B.put(FX.sinusoid(dtype)), "gm": None, "vt": None, "csf": None}
+        sigma_phi, expected = 4 * 2 * np.pi / 64, 22.0161
+        ref = FX.sinusoid_c0(dtype)
+    filt = B.empty((n, n, n), dtype)
+    h.mat_prop(dev["gm"], dev["wm"], dev["vt"], dev["csf"], None, filt)
+    h.phi_set([FX.TIL], sigma_phi, filt, sig_atlas)
+    c0 = B.empty((n, n, n), dtype)
+    h.phi_apply(c0, [1.0])
+    got = B.get(c0)
+    h.close()
+    return float(np.sqrt(np.sum(got.astype(np.float64) ** 2))), expected, rel(got, ref)

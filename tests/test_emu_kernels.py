@@ -59,3 +59,21 @@ def test_objective_gradient_hessian(B, dtype):
     assert r["its"][0] == r["its"][1] and r["h_its"][0] == r["h_its"][1], r
     assert r["J"] < 10 * tol and r["g_c0"] < 10 * tol and r["g6"] < 20 * tol, r
     assert r["h_y"] < 10 * tol and r["h_y_ponly"] < 10 * tol and r["h_k"] < 50 * tol, r
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_smoother(B, dtype):
+    e1, e2, e0 = Cs.case_smooth(B, (32, 32, 64), dtype)
+    assert e1 < 5 * EPS[np.dtype(dtype)] and e2 < 5 * EPS[np.dtype(dtype)] and e0 == 0.0
+
+
+def test_mat_prop(B):
+    ok, fs, fs_ref = Cs.case_mat_prop(B, 32, np.float32)
+    assert ok and fs == fs_ref
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_phi_apply_and_transpose(B, dtype):
+    e_apply, e_t, e_adj, zero_ok = Cs.case_phi(B, 32, dtype)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert e_apply < tol and e_t < tol and e_adj < 10 * tol and zero_ok

@@ -288,3 +288,36 @@ def test_ensemble_members_concurrent(B):
         ref = pde.solve_state(P["c0"], 0)
         assert its[i] == pde.ksp_state, (i, its[i], pde.ksp_state)
         assert Cs.rel(got, ref) < Cs.TOL[np.dtype(dtype)], (i, Cs.rel(got, ref))
+
+
+# ---- callers either side of the path: smoother, MatProp, Phi ----------------
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [64, (64, 128, 32), 256])
+def test_smoother(B, n, dtype):
+    e1, e2, e0 = Cs.case_smooth(B, n, dtype)
+    assert e1 < 5 * EPS[np.dtype(dtype)] and e2 < 5 * EPS[np.dtype(dtype)] and e0 == 0.0
+
+
+def test_mat_prop(B):
+    ok, fs, fs_ref = Cs.case_mat_prop(B, 64, np.float32)
+    assert ok and fs == fs_ref
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [64, 128])
+def test_phi_apply_and_transpose(B, n, dtype):
+    e_apply, e_t, e_adj, zero_ok = Cs.case_phi(B, n, dtype)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert e_apply < tol and e_t < tol and e_adj < 10 * tol and zero_ok
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("which", ["K2", "K3"])
+def test_reference_pins_K2_K3_on_the_gpu(B, which, dtype):
+    """src/test/simulator.cpp:41-42 (sinusoid, ||c0|| = 22.0161) and :94-95 (brain, ||c0|| =
+    4.09351): the reference's own known answers, computed end to end by the CUDA path from the
+    committed test data -- tissue smoothing, MatProp filter, Phi::apply."""
+    nrm, expected, err = Cs.case_K2_K3(B, dtype, which)
+    # Catch2 Approx: |a - b| < eps (1 + |b|), eps = 100 FLT_EPSILON
+    assert abs(nrm - expected) < 100 * np.finfo(np.float32).eps * (1 + expected) + 5e-5, (nrm, expected)
+    assert err < Cs.TOL[np.dtype(dtype)], err
