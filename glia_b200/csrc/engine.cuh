@@ -6,6 +6,7 @@
 //   DerivativeOperators::gradDiffusion/gradReaction  src/grad/DerivativeOperators.cpp:189-321
 #pragma once
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "engine_base.h"
@@ -14,6 +15,7 @@
 #include "sweeps.cuh"
 #include "sweeps_dist.cuh"
 #include "sweeps_pipe.cuh"
+#include "sweeps_v2.cuh"
 
 namespace glia {
 
@@ -53,6 +55,11 @@ inline int sm_count(int device) {
   int v = 0;
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
   return v;
+}
+inline size_t max_policy_window(int device) {
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) != cudaSuccess || v < 0) { cudaGetLastError(); v = 0; }
+  return (size_t)v;
 }
 inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
@@ -166,6 +173,8 @@ class Engine : public EngineBase {
   Comm comm;
   unsigned epoch = 0, rseq = 0;
   int nsm = 148;         // SMs of this device: grid size of the persistent (pipelined) sweeps
+  bool use_v2 = false;   // GLIA_RD_V2=1 selects the two-sequence packed FP32x2 D-sweeps (sweeps_v2.cuh); measured SLOWER at 256^3
+                         // (98-105 us vs 65-70 us: twice the shared-memory exchange traffic at E = 8)
   bool use_pipe = true;  // GLIA_RD_PIPE=0 selects the one-tile-per-CTA kernels (A/B measurements)
   int z_minb = 1;        // resident CTAs per SM the z second-derivative sweep is compiled for (GLIA_RD_ZMINB: 1, 3, 4).
                          // Measured at 256^3 f32: 1 (123 registers, no cap) 49.6 us; 3 / 4 (80 / 64 registers) 82 us
@@ -231,6 +240,9 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::stream_create(&st));
     nsm = rt::sm_count(device);
     if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_V2")) use_v2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_L2WIN")) use_window = std::atoi(e) != 0;
+    max_window = rt::max_policy_window(device);
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB512")) z_minb512 = std::atoi(e);
@@ -382,6 +394,19 @@ class Engine : public EngineBase {
     prof.after(slot, s);
     ++launches;
   }
+  // the same with `win` (one field) marked streaming for L2 in this launch; no-op for fields beyond the
+  // device's window limit (512^3: nothing fits in L2 anyway) or when GLIA_RD_L2WIN=0
+  size_t max_window = 0;
+  bool use_window = false;  // GLIA_RD_L2WIN=1 (measured: no gain at 256^3, see fft_core.cuh)
+  template <class... KA, class... A>
+  void LS(const void* win, const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
+    const size_t bytes = sizeof(T) * (size_t)nreal;
+    const bool ok = use_window && GLIA_L2_HINTS && win && bytes <= max_window;
+    const int slot = prof.before(tag, s);
+    simt::launch_streaming(ok ? win : nullptr, bytes, k, g, b, smem, s, args...);
+    prof.after(slot, s);
+    ++launches;
+  }
   void check_launch() {
     const char* e = simt::last_error();
     if (e) throw EngineError{std::string("kernel launch: ") + e};
@@ -443,12 +468,25 @@ class Engine : public EngineBase {
                          T* out2, double* pp, const int* done) {
     constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
     int nblk = 0;
+    if constexpr (std::is_same<T, float>::value) {
+      if (use_v2 && SL == 16) {  // packed FP32x2 line FFTs (sweeps_v2.cuh)
+        GLIA_DISPATCH_N(nline, {
+          const int ntiles = g.nchunk * g.n_outer;
+          const int cap = nsm * v2_ctas<N>();
+          nblk = ntiles < cap ? ntiles : cap;
+          LS(x, tag, ks2_deriv2_pipe<N, EPI, RowsS<float>, RowsS<float>, RowsS<float>, RowsS<float>>, dim3((unsigned)nblk),
+             dim3(N), v2_smem<N>(), st, ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1),
+             rows_s(g, out2), (const cplx<float>*)tw_for(nline, g), (float)alpha, pp, done);
+        });
+        return nblk;
+      }
+    }
     GLIA_DISPATCH_N(nline, {
       if (use_pipe && pipe_fits<T, N>()) {
         const int ntiles = g.nchunk * g.n_outer;
         const dim3 gr = grid_pipe<N>(ntiles);
         nblk = (int)gr.x;
-        L(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
+        LS(x, tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
           ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2), (const C*)tw_for(nline, g),
           alpha, pp, done);
       } else {

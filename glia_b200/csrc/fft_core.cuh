@@ -32,17 +32,58 @@ __device__ __forceinline__ cplx<T> cmulc(cplx<T> a, cplx<T> b) {  // a * conj(b)
   return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
 }
 
+// ---------------------------------------------- packed FP32x2 arithmetic ----
+// Blackwell (sm_100) issues two FP32 operations per instruction on a 64-bit register pair
+// (add / mul / fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2).  A cplx<float> IS such a pair, so complex
+// additions, subtractions and multiplications by a real scalar take one issue slot instead of two.
+// ncu (profiles/r1c_*): the single-precision sweeps are issue bound -- 70-83 % of their executed
+// instructions are the butterflies' FADD / FMUL / FFMA, 2.0-2.3 of 4 issue slots per cycle are
+// used, DRAM sits at 40-45 % -- so instruction count is what buys time.
+// MEASURED (profiles/r1d_f32x2_ab.txt): packing the butterflies' additions removed 17 % of the
+// D-sweeps' instructions (992 FADD -> 456 FADD2 + 144 FADD per tile and thread) and changed no
+// kernel's time by more than noise, the y sweep got 8 % slower: FADD2 holds the FMA pipe for two
+// issue cycles, and the sweeps are bound by their load -> transform -> store phase structure at
+// 16 resident warps per SM, not by issue slots.  Build option (-DGLIA_USE_F32X2), default off.
+#if !defined(GLIA_SIMT_EMU) && defined(GLIA_USE_F32X2)
+#define GLIA_F32X2 1
+__device__ __forceinline__ unsigned long long c_bits(cplx<float> v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ cplx<float> c_from(unsigned long long u) { return *reinterpret_cast<cplx<float>*>(&u); }
+__device__ __forceinline__ cplx<float> cadd(cplx<float> a, cplx<float> b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(b)));
+  return c_from(r);
+}
+__device__ __forceinline__ cplx<float> csub(cplx<float> a, cplx<float> b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(b)));
+  return c_from(r);
+}
+// a * (s, s)
+__device__ __forceinline__ cplx<float> cscale(cplx<float> a, float s) {
+  unsigned long long r;
+  const cplx<float> ss = {s, s};
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(ss)));
+  return c_from(r);
+}
+#else
+#define GLIA_F32X2 0
+#endif
+template <typename T>
+__device__ __forceinline__ cplx<T> cscale(cplx<T> a, T s) { return {a.x * s, a.y * s}; }
+
 // ------------------------------------------------- L2 residency hints ----
 // At 256^3 single precision one field is 67 MB and B200's L2 holds 126 MB: of the fields a PCG
-// iteration touches, exactly one fits next to the streams.  The sweeps therefore read every
-// operand that is consumed once per kernel (x, k, r, w, the last read of acc / shat / z) with
-// the evict-first policy (ld.global.cs), so that the field handed from one kernel to the next
-// (acc -> w -> shat -> z -> p) survives in L2 until its consumer runs.  Measured with
-// scripts/probes/l2_probe.cu (profiles/r1b_l2_probe.txt): a 4F read-modify-write kernel whose
-// accumulator was left in L2 by its producer runs at 7.4-7.6 TB/s effective against 5.5 TB/s
-// unhinted; pinning with evict_last or a persisting window adds nothing over this.
+// iteration touches, exactly one fits next to the streams.  With GLIA_L2_HINTS=1 the sweeps read
+// every operand that is consumed once per kernel (x, k, r, w, the last read of acc / shat) with the
+// evict-first policy (ld.global.cs), so that the field handed from one kernel to the next
+// (acc -> w -> shat -> z) survives in L2 until its consumer runs.
+// MEASURED (profiles/r1b_l2_probe.txt, profiles/r1c_l2_hints_ab.txt): a DRAM-bound 4F streaming
+// kernel gains 25-30% from this (7.5 TB/s effective against 5.5), but the sweep kernels do not --
+// they are issue / latency bound, not DRAM bound, at this size (65 us for 4F where DRAM needs 41) --
+// and evict-first STORES of sub-sector pieces (the z sweeps write 64-byte runs) tripled kz_r2c's
+// time.  Default OFF; kept as a build option for grids whose sweeps become DRAM bound.
 #ifndef GLIA_L2_HINTS
-#define GLIA_L2_HINTS 1
+#define GLIA_L2_HINTS 0
 #endif
 #if defined(GLIA_SIMT_EMU) || !GLIA_L2_HINTS
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return *p; }
@@ -67,6 +108,17 @@ __device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) {
   __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
 #endif
+
+// software prefetch of one 128-byte line into L1 (for operands an epilogue reads long after the
+// kernel starts: zero registers held across the transform)
+template <typename V>
+__device__ __forceinline__ void prefetch_l1(const V* p) {
+#if !defined(GLIA_SIMT_EMU)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 
 // ---------------------------------------------------------------- plans ----
 template <int N> struct FftPlan;
@@ -121,6 +173,30 @@ __device__ __forceinline__ cplx<T> twmul_const(cplx<T> d) {
 }
 
 // --------------------------------------------- in-register radix-R DFT ----
+#if GLIA_F32X2
+template <typename T, int R, int SIGN, int J>
+__device__ __forceinline__ void dif_bf(cplx<T>* v) {
+  constexpr int H = R / 2;
+  constexpr int j32 = (J % R) * (32 / R);
+  cplx<T> a = v[J], b = v[J + H];
+  v[J] = cadd(a, b);
+  if constexpr (j32 == 8) {
+    // (a - b) * (SIGN i) written as two operand-swapped subtractions, so that no negation is needed
+    // (the packed add / sub results feed other packed operations, which take no sign modifiers in PTX)
+    if constexpr (SIGN > 0) v[J + H] = {b.y - a.y, a.x - b.x};
+    else v[J + H] = {a.y - b.y, b.x - a.x};
+  } else if constexpr (j32 == 0 || j32 == 16 || j32 == 24) {
+    v[J + H] = twmul_const<T, R, J, SIGN>(csub(a, b));
+  } else {
+    // d (c + i s) = (d.x c, d.y c) + (-s d.y, s d.x): one scaling of the pair + two FMAs
+    constexpr T c = (T)cos32(j32);
+    constexpr T s = (T)(SIGN * sin32(j32));
+    const cplx<T> d = csub(a, b);
+    const cplx<T> dc = cscale(d, c);
+    v[J + H] = {dc.x - s * d.y, dc.y + s * d.x};
+  }
+}
+#else
 template <typename T, int R, int SIGN, int J>
 __device__ __forceinline__ void dif_bf(cplx<T>* v) {
   constexpr int H = R / 2;
@@ -128,6 +204,7 @@ __device__ __forceinline__ void dif_bf(cplx<T>* v) {
   v[J] = cadd(a, b);
   v[J + H] = twmul_const<T, R, J, SIGN>(csub(a, b));
 }
+#endif
 template <typename T, int R, int SIGN, int... J>
 __device__ __forceinline__ void dif_level(cplx<T>* v, std::integer_sequence<int, J...>) {
   (dif_bf<T, R, SIGN, J>(v), ...);

@@ -20,22 +20,28 @@ enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_DIVERGED_ITS = -3, KS
 
 template <int NV>
 __device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int n, double (&out)[NV]) {
-  // fixed-order (deterministic) two-level sum by one CTA of 256 threads
+  // fixed-order (deterministic) two-level sum by one CTA; the first min(blockDim, 256) threads gather
+  // with that stride (256 for the scalar kernels and the 256-thread sweeps), then a binary tree
   __shared__ double sh[256 * NV];
-  const int tid = threadIdx.x;
-  double acc[NV];
-  GLIA_UNROLL
-  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-  for (int j = tid; j < n; j += 256)
+  const int tid = threadIdx.x, nt = (int)blockDim.x;
+  const int nth = nt < 256 ? nt : 256;
+  for (int j = tid; j < 256 * NV; j += nt) sh[j] = 0.0;
+  __syncthreads();
+  if (tid < nth) {
+    double acc[NV];
     GLIA_UNROLL
-    for (int i = 0; i < NV; ++i) acc[i] += partial[(size_t)j * NV + i];
-  GLIA_UNROLL
-  for (int i = 0; i < NV; ++i) sh[tid * NV + i] = acc[i];
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int j = tid; j < n; j += nth)
+      GLIA_UNROLL
+      for (int i = 0; i < NV; ++i) acc[i] += partial[(size_t)j * NV + i];
+    GLIA_UNROLL
+    for (int i = 0; i < NV; ++i) sh[tid * NV + i] = acc[i];
+  }
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s)
+    for (int q = tid; q < s; q += nt)
       GLIA_UNROLL
-      for (int i = 0; i < NV; ++i) sh[tid * NV + i] += sh[(tid + s) * NV + i];
+      for (int i = 0; i < NV; ++i) sh[q * NV + i] += sh[(q + s) * NV + i];
     __syncthreads();
   }
   GLIA_UNROLL
@@ -43,6 +49,30 @@ __device__ __forceinline__ void sum_partials(const double* __restrict__ partial,
   __syncthreads();
 }
 
+template <typename T>
+__device__ __forceinline__ void pcg_alpha_finish(double dpi, double* scal, int* iscal) {
+  scal[S_DPI] = dpi;
+  scal[S_BETAOLD] = scal[S_BETA];
+  scal[S_A] = (double)(T)(scal[S_BETA] / dpi);
+  if (!(dpi > 0.0)) { iscal[I_REASON] = KSP_DIVERGED_INDEFINITE_MAT; iscal[I_TOTAL] += iscal[I_ITS]; iscal[I_DONE] = 1; }
+}
+template <typename T>
+__device__ __forceinline__ void pcg_beta_finish(const double (&rz)[2], double* scal, int* iscal, int maxit, double dtol) {
+  const double dp = sqrt(rz[0]);
+  scal[S_DP] = dp;
+  const int its = iscal[I_ITS] + 1;
+  iscal[I_ITS] = its;
+  int done = 0, reason = 0;
+  if (dp != dp) { done = 1; reason = KSP_DIVERGED_NANORINF; }
+  else if (dp <= scal[S_TTOL]) { done = 1; reason = KSP_CONVERGED_RTOL; }
+  else if (dp >= dtol * scal[S_RNORM0]) { done = 1; reason = KSP_DIVERGED_DTOL; }
+  else if (its >= maxit) { done = 1; reason = KSP_DIVERGED_ITS; }
+  const double beta = rz[1];
+  scal[S_B] = (double)(T)(beta / scal[S_BETAOLD]);
+  scal[S_BETA] = beta;
+  iscal[I_REASON] = reason;
+  if (done) { iscal[I_DONE] = 1; iscal[I_TOTAL] += its; }
+}
 // KSPConvergedDefault at iteration 0 with a non-zero initial guess:
 //   rnorm0 = ||M^-1 b|| (or dp if that is 0), ttol = max(rtol*rnorm0, abstol), test dp <= ttol.
 static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
@@ -79,12 +109,7 @@ __global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal, 
   double d[1];
   sum_partials<1>(ppw, n, d);
   peer_allreduce<1>(comm, epoch, seq, d);
-  if (threadIdx.x == 0) {
-    scal[S_DPI] = d[0];
-    scal[S_BETAOLD] = scal[S_BETA];
-    scal[S_A] = (double)(T)(scal[S_BETA] / d[0]);
-    if (!(d[0] > 0.0)) { iscal[I_REASON] = KSP_DIVERGED_INDEFINITE_MAT; iscal[I_TOTAL] += iscal[I_ITS]; iscal[I_DONE] = 1; }
-  }
+  if (threadIdx.x == 0) pcg_alpha_finish<T>(d[0], scal, iscal);
 }
 
 // after z = M^-1 r: dp = ||z||, its++, convergence test, beta = <r,z>, b = beta/betaold
@@ -95,22 +120,7 @@ __global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, i
   double rz[2];
   sum_partials<2>(prz, n, rz);
   peer_allreduce<2>(comm, epoch, seq, rz);
-  if (threadIdx.x == 0) {
-    const double dp = sqrt(rz[0]);
-    scal[S_DP] = dp;
-    const int its = iscal[I_ITS] + 1;
-    iscal[I_ITS] = its;
-    int done = 0, reason = 0;
-    if (dp != dp) { done = 1; reason = KSP_DIVERGED_NANORINF; }
-    else if (dp <= scal[S_TTOL]) { done = 1; reason = KSP_CONVERGED_RTOL; }
-    else if (dp >= dtol * scal[S_RNORM0]) { done = 1; reason = KSP_DIVERGED_DTOL; }
-    else if (its >= maxit) { done = 1; reason = KSP_DIVERGED_ITS; }
-    const double beta = rz[1];
-    scal[S_B] = (double)(T)(beta / scal[S_BETAOLD]);
-    scal[S_BETA] = beta;
-    iscal[I_REASON] = reason;
-    if (done) { iscal[I_DONE] = 1; iscal[I_TOTAL] += its; }
-  }
+  if (threadIdx.x == 0) pcg_beta_finish<T>(rz, scal, iscal, maxit, dtol);
 }
 
 // iteration `it` (1-based): x += a p ; if not converged p = z + b p.
@@ -125,10 +135,9 @@ __global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const d
   const int done = iscal[I_DONE];
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    // x and z are touched once per iteration (streamed); p stays in L2 for the next D-apply
     const T pv = p[i];
-    st_stream(x + i, ld_stream(x + i) + a * pv);
-    if (!done) p[i] = ld_stream(z + i) + b * pv;
+    x[i] = x[i] + a * pv;
+    if (!done) p[i] = z[i] + b * pv;
   }
 }
 

@@ -47,6 +47,39 @@ inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStr
   }
   k<<<grid, block, smem, st>>>(static_cast<KA>(args)...);
 }
+// the same launch with an access-policy window: every access of this kernel into [win, win + bytes)
+// is treated as streaming (evict-first) by L2.  Used for operands that LDGSTS stages (cp.async
+// carries no usable per-instruction policy on sm_100a with this toolchain).
+template <class... KA, class... A>
+inline void launch_streaming(const void* win, size_t bytes, void (*k)(KA...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t st, A... args) {
+  if (!win || !bytes) return launch(k, grid, block, smem, st, args...);
+  if (smem > 32 * 1024) {  // same opt-in as launch()
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    auto& m = smem_attr_cache();
+    auto it = m.find((const void*)k);
+    if (it == m.end() || it->second < smem) {
+      cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      m[(const void*)k] = smem;
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+  at[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(win);
+  at[0].val.accessPolicyWindow.num_bytes = bytes;
+  at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+  at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyStreaming;
+  at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, static_cast<KA>(args)...);
+}
 inline const char* last_error() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

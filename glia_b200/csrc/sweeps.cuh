@@ -21,7 +21,12 @@
 namespace glia {
 
 // ------------------------------------------------------------ helpers ----
-static constexpr int SL = 16;  // complex columns (lanes) per S tile
+// complex columns (lanes) per S tile: 16 = 128-byte rows in single precision.  GLIA_SL=8 (64-byte
+// rows, half-size CTAs, twice as many independent barrier groups per SM) is a build-time A/B option.
+#ifndef GLIA_SL
+#define GLIA_SL 16
+#endif
+static constexpr int SL = GLIA_SL;
 
 // occupancy hint of the S kernels: two resident CTAs per SM for single-precision tiles of <= 256 threads
 template <typename T, int N>
@@ -560,7 +565,7 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
       if (PRO) {
         rv.x = rv.x - aa * ld_stream(w + la + pos);
         rv.y = rv.y - aa * ld_stream(w + lb + pos);
-        if (z.active) { st_stream(r + la + pos, rv.x); st_stream(r + lb + pos, rv.y); }
+        if (z.active) { r[la + pos] = rv.x; r[lb + pos] = rv.y; }
       }
       v[g * F::R(0) + a] = rv;
     }
@@ -614,6 +619,12 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
   const long la = z.pair * 2 * N, lb = la + N;
   const long oa = z.pair * 2 * (N / 2), ob = oa + N / 2;
   AmZ am = z.am();
+  if (EPI && r) {
+    // the <r,z> epilogue reads r only after the whole inverse transform: start the two lines (2N
+    // contiguous values) towards L1 now (ncu: 49 % of this kernel's stall samples sat on those loads)
+    constexpr int PER = 128 / (int)sizeof(T);
+    for (int i = z.t; i < 2 * N / PER; i += F::TPL) prefetch_l1(r + la + i * PER);
+  }
   sy();
   GLIA_UNROLL
   for (int j = 0; j < E / 2; ++j) {

@@ -15,6 +15,8 @@
 //   DiffusionSolver    include/pde/DiffusionSolver.h:7-42        glia::host::DiffusionSolver
 //   PdeOperatorsRD     include/pde/PdeOperators.h:10-77          glia::host::PdeOperatorsRD
 //   DerivativeOperatorsRD include/grad/DerivativeOperators.h:9-81 glia::host::DerivativeOperatorsRD
+//   Phi                include/mat/Phi.h (on-the-fly mode)       glia::host::Phi
+//   MatProp            include/mat/MatProp.h                     glia::host::MatProp
 //
 // Header-only; needs the CUDA runtime (device memory of the Vec shim) and -lglia_rd.
 #pragma once
@@ -112,6 +114,10 @@ class SpectralOperators {
   ErrorCode computeDivergence(Vec<Real>& div, const Vec<Real>& dx, const Vec<Real>& dy, const Vec<Real>& dz) {
     return glia_rd_divergence(h_, div.array(), dx.array(), dy.array(), dz.array());
   }
+  // weierstrassSmoother(wc, c, params, sigma)  (SpectralOperators.cpp:263-381); wc may alias c
+  ErrorCode weierstrassSmoother(Vec<Real>& wc, const Vec<Real>& c, double sigma) {
+    return glia_rd_smooth(h_, wc.array(), c.array(), sigma);
+  }
   std::string lastError() const { return glia_rd_last_error(h_); }
 
  private:
@@ -122,8 +128,46 @@ class SpectralOperators {
 // tissue maps (MatProp fields the coefficients are built from, src/mat/MatProp.cpp)
 template <typename Real>
 struct MatProp {
-  std::shared_ptr<Vec<Real>> wm_, gm_, csf_;
+  std::shared_ptr<Vec<Real>> wm_, gm_, csf_, vt_, bg_, filter_;
   double filter_sum = 0;  // sum of the brain mask (MatProp.cpp:180-185)
+  // setValuesCustom(gm, wm, csf, vt, bg, params)  (MatProp.cpp:135-201): clip, bg, filter
+  ErrorCode setValuesCustom(SpectralOperators<Real>& spec_ops, long nl) {
+    if (!bg_) bg_ = std::make_shared<Vec<Real>>(nl, nl);
+    if (!filter_) filter_ = std::make_shared<Vec<Real>>(nl, nl);
+    return glia_rd_mat_prop(spec_ops.handle(), gm_ ? gm_->array() : nullptr, wm_ ? wm_->array() : nullptr,
+                            vt_ ? vt_->array() : nullptr, csf_ ? csf_->array() : nullptr, bg_->array(), filter_->array(),
+                            &filter_sum);
+  }
+};
+
+// Phi in on-the-fly mode (include/mat/Phi.h, src/mat/Phi.cpp:24-120, 324-434)
+template <typename Real>
+class Phi {
+ public:
+  Phi(std::shared_ptr<Parameters> params, std::shared_ptr<SpectralOperators<Real>> spec_ops)
+      : params_(params), spec_ops_(spec_ops) {}
+  // setGaussians / setValues: centres (radians), sigma, the MatProp filter, smoothing_factor
+  ErrorCode setValues(const std::vector<double>& centers, double sigma, const MatProp<Real>* mat_prop,
+                      double smoothing_factor = 1.0) {
+    np_ = (int)(centers.size() / 3);
+    sigma_ = sigma;
+    const double sigma_smooth = smoothing_factor * 2.0 * M_PI / params_->n[0];  // Phi.cpp:338
+    return glia_rd_phi_set(spec_ops_->handle(), np_, centers.data(), sigma,
+                           (mat_prop && mat_prop->filter_) ? mat_prop->filter_->array() : nullptr, sigma_smooth);
+  }
+  ErrorCode apply(Vec<Real>& out, const std::vector<double>& p) {  // Phi::apply(out, p)
+    return glia_rd_phi_apply(spec_ops_->handle(), out.array(), p.data());
+  }
+  ErrorCode applyTranspose(std::vector<double>& pout, const Vec<Real>& in) {  // Phi::applyTranspose(pout, in)
+    pout.assign((size_t)np_, 0.0);
+    return glia_rd_phi_apply_transpose(spec_ops_->handle(), pout.data(), in.array());
+  }
+  int np_ = 0;
+  double sigma_ = 0;
+
+ private:
+  std::shared_ptr<Parameters> params_;
+  std::shared_ptr<SpectralOperators<Real>> spec_ops_;
 };
 
 template <typename Real>

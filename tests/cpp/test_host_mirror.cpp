@@ -80,6 +80,40 @@ void evaluating_objective_function() {
   REQUIRE(J2 == J);
 }
 
+template <typename Real>
+void applying_phi() {
+  // Phi in on-the-fly mode through the host classes: c(0) = Phi p is bounded by max(p) (every basis
+  // function is scaled by the common maximum), and <Phi p, f> == <p, Phi^T f>.
+  auto params = std::make_shared<Parameters>();
+  params->n[0] = params->n[1] = params->n[2] = 64;
+  auto spec_ops = std::make_shared<SpectralOperators<Real>>(params);
+  const long nl = params->nl();
+  MatProp<Real> mat;
+  mat.wm_ = std::make_shared<Vec<Real>>(nl, nl);
+  mat.wm_->set((Real)0.5);  // white matter everywhere: filter = 1
+  REQUIRE(mat.setValuesCustom(*spec_ops, nl) == 0);
+  REQUIRE(mat.filter_sum == (double)nl);
+  Phi<Real> phi(params, spec_ops);
+  const std::vector<double> centers = {3.0, 3.2, 2.9, 2.5, 3.0, 3.4};
+  REQUIRE(phi.setValues(centers, 2 * M_PI / 32, &mat) == 0);
+  Vec<Real> c0(nl, nl), f(nl, nl), wf(nl, nl);
+  const std::vector<double> p = {0.7, -0.4};
+  REQUIRE(phi.apply(c0, p) == 0);
+  createTestFunction(f, *params);
+  REQUIRE(spec_ops->weierstrassSmoother(wf, f, 2 * M_PI / 64) == 0);
+  std::vector<double> pt;
+  REQUIRE(phi.applyTranspose(pt, wf) == 0);
+  std::vector<Real> hc((size_t)nl), hf((size_t)nl);
+  c0.to_host(hc.data());
+  wf.to_host(hf.data());
+  double lhs = 0, cmax = 0;
+  for (long i = 0; i < nl; ++i) { lhs += (double)hc[i] * (double)hf[i]; cmax = std::fmax(cmax, std::fabs((double)hc[i])); }
+  const double rhs = p[0] * pt[0] + p[1] * pt[1];
+  std::printf("  [phi/%s] <Phi p, f> = %.8e  <p, Phi^T f> = %.8e  max|c0| = %.6f\n", sizeof(Real) == 4 ? "f32" : "f64", lhs, rhs, cmax);
+  REQUIRE(std::fabs(lhs - rhs) <= (sizeof(Real) == 4 ? 1e-4 : 1e-10) * std::fabs(lhs));
+  REQUIRE(cmax <= 0.7 * (1 + 1e-5) && cmax > 0.3);
+}
+
 int main() {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("no CUDA device\n"); return 77; }
@@ -89,6 +123,9 @@ int main() {
   std::printf("Evaluating objective function\n");
   evaluating_objective_function<float>();
   evaluating_objective_function<double>();
+  std::printf("Applying Phi\n");
+  applying_phi<float>();
+  applying_phi<double>();
   std::printf("%s (%d failure(s))\n", failures ? "FAILED" : "ALL PASSED", failures);
   return failures;
 }

@@ -120,6 +120,11 @@ template <class... KA, class... A>
 inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t, A... args) {
   emu::launch(grid, block, smem, [=]() { k(args...); });
 }
+template <class... KA, class... A>
+inline void launch_streaming(const void*, size_t, void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             A... args) {
+  launch(k, grid, block, smem, st, args...);
+}
 inline const char* last_error() { return nullptr; }
 }  // namespace simt
 
@@ -167,6 +172,7 @@ inline void ipc_free(void* p, size_t n, const unsigned char* handle) {
   if (handle && handle[0]) shm_unlink((const char*)handle);
 }
 inline int sm_count(int) { return 3; }
+inline size_t max_policy_window(int) { return 0; }
 inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
 inline void stream_destroy(cudaStream_t) {}
 inline const char* err_string(int) { return "emu"; }

@@ -321,3 +321,14 @@ def test_reference_pins_K2_K3_on_the_gpu(B, which, dtype):
     # Catch2 Approx: |a - b| < eps (1 + |b|), eps = 100 FLT_EPSILON
     assert abs(nrm - expected) < 100 * np.finfo(np.float32).eps * (1 + expected) + 5e-5, (nrm, expected)
     assert err < Cs.TOL[np.dtype(dtype)], err
+
+
+def test_two_sequence_packed_sweeps_match(B, monkeypatch):
+    """GLIA_RD_V2=1 selects the two-sequence packed FP32x2 D-sweeps (sweeps_v2.cuh; an A/B option,
+    slower than the default at 256^3): same parity bar as the default path."""
+    monkeypatch.setenv("GLIA_RD_V2", "1")
+    r = Cs.case_forward_adjoint(B, 64, np.float32, nt=2, dt=0.04)
+    assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1]
+    assert r["cT"] < 1e-5 and r["p0"] < 1e-5
+    e1, e2, budget = Cs.case_apply_D(B, 128, np.float32, False)
+    assert e1 < budget and e2 < budget
