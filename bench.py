@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -58,6 +59,7 @@ def parse():
     ap.add_argument("--kappa", type=float, default=0.01)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 gradient / Hessian / Phi timings")
     ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     a = ap.parse_args()
@@ -393,6 +395,28 @@ def run_b200(a):
         "roofline": roofline,
         "kernels": kern,
     }
+    if world == 1 and not a.no_extras:
+        # one evaluateObjectiveAndGradient, one Gauss-Newton Hessian product with
+        # diffusivity inversion, and Phi (np = 8 Gaussians) either side of them -- reported, not the headline
+        gfield, yfield = torch.empty_like(c0d), torch.empty_like(c0d)
+        h.timer_start()
+        og = h.objective_gradient(c0d, d1, wm, gm, csf, beta=1e-4, g_c0=gfield)
+        t_grad = h.timer_stop_ms()
+        h.set_secondary_tissue(wm, gm, csf, 1.0, 0.0, 0.0)
+        h.timer_start()
+        _, hits = h.hessian_matvec(c0d, yfield, wm, gm, csf, beta=1e-4, diffusivity_inversion=True)
+        t_hess = h.timer_stop_ms()
+        ctr = [(math.pi + dx, math.pi + dy, math.pi + dz) for dx in (-0.25, 0.25) for dy in (-0.25, 0.25) for dz in (-0.25, 0.25)]
+        h.phi_set(ctr, 2 * math.pi / 64, put(atlas["filter"]), 2 * math.pi / a.n)
+        h.timer_start()
+        h.phi_apply(yfield, [1.0] * 8)
+        t_phi = h.timer_stop_ms()
+        h.timer_start()
+        h.phi_apply_transpose(gfield)
+        t_phit = h.timer_stop_ms()
+        line["config3"] = {"objective_gradient_ms": t_grad, "objective_gradient_pcg_its": list(og["its"]),
+                           "hessian_matvec_kappa_ms": t_hess, "hessian_matvec_pcg_its": list(hits),
+                           "phi_apply_np8_ms": t_phi, "phi_apply_transpose_np8_ms": t_phit}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         run, cores, desc = cpu_reference_sample(a, atlas, c0, a.ref_nt)
         t0 = time.perf_counter()

@@ -57,6 +57,9 @@ SIGNATURES = {
     "glia_rd_phi_set": (_I, [_P, _I, C.POINTER(_D), _D, _P, _D]),
     "glia_rd_phi_apply": (_I, [_P, _P, C.POINTER(_D)]),
     "glia_rd_phi_apply_transpose": (_I, [_P, C.POINTER(_D), _P]),
+    "glia_rd_data_in": (_I, [_P, C.c_char_p, _P]),
+    "glia_rd_data_out": (_I, [_P, C.c_char_p, _P]),
+    "glia_rd_split_segmentation": (_I, [_P, _P, C.POINTER(_I), _P, _P, _P, _P]),
     "glia_rd_probe_xsweep": (_I, [_P, _I, _I, _I, C.POINTER(_D)]),
     "glia_rd_profile_begin": (_I, [_P]),
     "glia_rd_profile_end": (_I, [_P, C.c_char_p, _I]),

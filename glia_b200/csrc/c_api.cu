@@ -220,6 +220,24 @@ int glia_rd_phi_apply_transpose(glia_rd_t* h, double* pout, const void* in) {
     E.v_phi_apply_transpose(pout, in);
   });
 }
+int glia_rd_data_in(glia_rd_t* h, const char* path, void* field) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!path || !field) throw EngineError{"data_in: null argument"};
+    E.v_data_in(path, field);
+  });
+}
+int glia_rd_data_out(glia_rd_t* h, const char* path, const void* field) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!path || !field) throw EngineError{"data_out: null argument"};
+    E.v_data_out(path, field);
+  });
+}
+int glia_rd_split_segmentation(glia_rd_t* h, const void* seg, const int labels[4], void* wm, void* gm, void* vt, void* csf) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!seg || !labels) throw EngineError{"split_segmentation: null argument"};
+    E.v_split_segmentation(seg, labels, wm, gm, vt, csf);
+  });
+}
 int glia_rd_probe_xsweep(glia_rd_t* h, int what, int local_mask, int reps, double* ms_per_sweep) {
   return guarded(h, [&](EngineBase& E) {
     const double t = E.v_probe(what, local_mask, reps);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "engine_base.h"
+#include "netcdf_io.h"
 #include "pointwise.cuh"
 #include "phi.cuh"
 #include "sweeps.cuh"
@@ -1153,6 +1154,29 @@ class Engine : public EngineBase {
     for (int i = 0; i < phi_np; ++i) pout[i] = (double)((T)dots[i] * alpha);
   }
 
+  // ------------------------------------------------ data in / out, labels ----
+  // dataIn (src/utils/IO.cpp:511-538): variable "data" of a NetCDF classic file -> this rank's block
+  void data_in(const char* path, T* field) {
+    std::vector<T> host((size_t)nreal);
+    try { nc::read_block<T>(path, n, rank * n0l, n0l, host.data()); }
+    catch (const nc::Error& e) { throw EngineError{e.msg}; }
+    GLIA_CHECK(rt::h2d(field, host.data(), sizeof(T) * nreal, st));
+    sync();
+  }
+  // dataOut (IO.cpp:540-612): CDF-2 file, dims x y z, NC_FLOAT / NC_DOUBLE; every rank writes its rows
+  void data_out(const char* path, const T* field) {
+    std::vector<T> host((size_t)nreal);
+    GLIA_CHECK(rt::d2h(host.data(), field, sizeof(T) * nreal, st));
+    sync();
+    try { nc::write_block<T>(path, n, rank * n0l, n0l, host.data()); }
+    catch (const nc::Error& e) { throw EngineError{e.msg}; }
+  }
+  void split_segmentation(const T* seg, const int labels[4], T* wm, T* gm, T* vt, T* csf) {
+    L("k_split_seg", k_split_seg<T>, grid_pw(nreal), dim3(256), 0, st, nreal, seg, labels[0], labels[1], labels[2], labels[3],
+      wm, gm, vt, csf);
+    sync();
+  }
+
   // ------------------------------------------ forward + adjoint entries ----
   // solveState(0), p_T = -(c(T) - d1) (O = I; DerivativeOperatorsRD.cpp:156-161), solveAdjoint(1)
   void forward_adjoint(const T* c0, const T* d1, T* cT, T* p0out, int* ks, int* ka) {
@@ -1271,6 +1295,11 @@ class Engine : public EngineBase {
   }
   void v_phi_apply(void* out, const double* p) override { phi_apply((T*)out, p); }
   void v_phi_apply_transpose(double* pout, const void* in) override { phi_apply_transpose(pout, (const T*)in); }
+  void v_data_in(const char* path, void* field) override { data_in(path, (T*)field); }
+  void v_data_out(const char* path, const void* field) override { data_out(path, (const T*)field); }
+  void v_split_segmentation(const void* seg, const int labels[4], void* wm, void* gm, void* vt, void* csf) override {
+    split_segmentation((const T*)seg, labels, (T*)wm, (T*)gm, (T*)vt, (T*)csf);
+  }
   double v_probe(int what, int mask, int reps) override { return probe_xsweep(what, mask, reps); }
   void v_profile_begin() override { sync(); prof.begin(); }
   std::string v_profile_end() override { return prof.end(st); }

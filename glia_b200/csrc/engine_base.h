@@ -50,6 +50,9 @@ class EngineBase {
   virtual void v_phi_set(int np, const double* centers, double sigma_phi, const void* filter, double sigma_smooth) = 0;
   virtual void v_phi_apply(void* out, const double* p) = 0;
   virtual void v_phi_apply_transpose(double* pout, const void* in) = 0;
+  virtual void v_data_in(const char* path, void* field) = 0;
+  virtual void v_data_out(const char* path, const void* field) = 0;
+  virtual void v_split_segmentation(const void* seg, const int labels[4], void* wm, void* gm, void* vt, void* csf) = 0;
   virtual double v_probe(int what, int local_mask, int reps) = 0;
   virtual void v_profile_begin() = 0;
   virtual std::string v_profile_end() = 0;

@@ -245,4 +245,19 @@ __global__ void k_mat_prop(long n, T* gm, T* wm, T* vt, T* csf, T* bg, T* filter
   }
 }
 
+// splitSegmentation, atlas form (src/utils/Utils.cpp:592-657 with tu == ed == nullptr): one-hot
+// tissue maps from a label image; a label <= 0 leaves its map zero; null outputs are skipped.
+template <typename T>
+__global__ void k_split_seg(long n, const T* __restrict__ seg, int wm_l, int gm_l, int vt_l, int csf_l, T* wm, T* gm, T* vt,
+                            T* csf) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T s = seg[i];
+    if (wm) wm[i] = (wm_l > 0 && s == (T)wm_l) ? (T)1 : (T)0;
+    if (gm) gm[i] = (gm_l > 0 && s == (T)gm_l) ? (T)1 : (T)0;
+    if (vt) vt[i] = (vt_l > 0 && s == (T)vt_l) ? (T)1 : (T)0;
+    if (csf) csf[i] = (csf_l > 0 && s == (T)csf_l) ? (T)1 : (T)0;
+  }
+}
+
 }  // namespace glia

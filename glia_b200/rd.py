@@ -236,6 +236,20 @@ class RDHandle:
         self._ck(self.lib.glia_rd_phi_apply_transpose(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), _ptr(inp)))
         return out
 
+    # -- data in / out, segmentation labels ------------------------------------------------
+    def data_in(self, path, field):
+        """dataIn: NetCDF classic file (variable ``data``, dims x y z) -> device field (local rows)."""
+        self._ck(self.lib.glia_rd_data_in(self._h, str(path).encode(), _ptr(field)))
+
+    def data_out(self, path, field):
+        """dataOut: device field -> CDF-2 file laid out like the reference's."""
+        self._ck(self.lib.glia_rd_data_out(self._h, str(path).encode(), _ptr(field)))
+
+    def split_segmentation(self, seg, labels, wm=None, gm=None, vt=None, csf=None):
+        """splitSegmentation (atlas form): labels = (wm, gm, vt, csf)."""
+        lab = (C.c_int * 4)(*[int(v) for v in labels])
+        self._ck(self.lib.glia_rd_split_segmentation(self._h, _ptr(seg), lab, _ptr(wm), _ptr(gm), _ptr(vt), _ptr(csf)))
+
     # -- per-kernel profile -----------------------------------------------------------
     def profile_begin(self):
         self._ck(self.lib.glia_rd_profile_begin(self._h))

@@ -182,6 +182,20 @@ int glia_rd_phi_apply(glia_rd_t* h, void* out, const double* p);
 /* Phi::applyTranspose (Phi.cpp:385-434): pout_i = <phi_i, in> / max_i max(phi_i) (HOST, np). */
 int glia_rd_phi_apply_transpose(glia_rd_t* h, double* pout, const void* in);
 
+/* ---- data formats either side of the path ---------------------------------- */
+/* dataIn (src/utils/IO.cpp:511-538, PnetCDF there): reads variable "data" (dims x, y, z; any numeric
+ * nc_type; NetCDF classic CDF-1 / CDF-2 / CDF-5 headers) into the device field -- a slab handle reads
+ * its own x rows, like ncmpi_get_vara_all with the rank's istart / isize. */
+int glia_rd_data_in(glia_rd_t* h, const char* path, void* field);
+/* dataOut (IO.cpp:540-612): writes the device field as a CDF-2 file laid out like the reference's
+ * (dims x y z, "data" NC_FLOAT / NC_DOUBLE, global attribute "CDF-5 mode" = 0); collective on slab
+ * handles (every rank writes its rows). */
+int glia_rd_data_out(glia_rd_t* h, const char* path, const void* field);
+/* splitSegmentation, atlas form (src/utils/Utils.cpp:592-657 with tu == ed == nullptr): one-hot maps
+ * for labels = {wm, gm, vt, csf} (a label <= 0 gives a zero map; null outputs are skipped). */
+int glia_rd_split_segmentation(glia_rd_t* h, const void* seg, const int labels[4], void* wm, void* gm, void* vt,
+                               void* csf);
+
 /* ---- per-kernel profile (CUDA events around every launch on the handle's stream) ---- */
 /* begin: start recording; end: stop, and write one "tag launches total_ms" line per kernel
  * family into buf (NUL-terminated, truncated to buflen).  Replaces the reference's

@@ -140,6 +140,23 @@ struct MatProp {
   }
 };
 
+// dataIn / dataOut (src/utils/IO.cpp:511-640) and splitSegmentation, atlas form (src/utils/Utils.cpp:592-657)
+template <typename Real>
+ErrorCode dataIn(Vec<Real>& A, SpectralOperators<Real>& spec_ops, const std::string& fname) {
+  return glia_rd_data_in(spec_ops.handle(), fname.c_str(), A.array());
+}
+template <typename Real>
+ErrorCode dataOut(const Vec<Real>& A, SpectralOperators<Real>& spec_ops, const std::string& fname) {
+  return glia_rd_data_out(spec_ops.handle(), fname.c_str(), A.array());
+}
+template <typename Real>
+ErrorCode splitSegmentation(const Vec<Real>& seg, Vec<Real>* wm, Vec<Real>* gm, Vec<Real>* vt, Vec<Real>* csf,
+                            SpectralOperators<Real>& spec_ops, const std::vector<int>& labels) {
+  const int lab[4] = {labels[0], labels[1], labels[2], labels.size() > 3 ? labels[3] : 0};
+  return glia_rd_split_segmentation(spec_ops.handle(), seg.array(), lab, wm ? wm->array() : nullptr, gm ? gm->array() : nullptr,
+                                    vt ? vt->array() : nullptr, csf ? csf->array() : nullptr);
+}
+
 // Phi in on-the-fly mode (include/mat/Phi.h, src/mat/Phi.cpp:24-120, 324-434)
 template <typename Real>
 class Phi {

@@ -332,3 +332,26 @@ def test_two_sequence_packed_sweeps_match(B, monkeypatch):
     assert r["cT"] < 1e-5 and r["p0"] < 1e-5
     e1, e2, budget = Cs.case_apply_D(B, 128, np.float32, False)
     assert e1 < budget and e2 < budget
+
+
+def test_netcdf_round_trip_and_label_split_on_device(B, tmp_path):
+    """glia_rd_data_out / data_in with device fields (CDF-2 file readable by scipy) and the label split."""
+    import scipy.io
+    from golden import fixtures as FX
+    seg = FX.atlas_labels().astype(np.float32)
+    h = B.handle(64, np.float32)
+    sd = B.put(seg)
+    p = str(tmp_path / "seg.nc")
+    h.data_out(p, sd)
+    f = scipy.io.netcdf_file(p, "r", mmap=False)
+    assert np.array_equal(f.variables["data"].data, seg)
+    f.close()
+    back = B.empty(seg.shape, np.float32)
+    h.data_in(p, back)
+    assert np.array_equal(B.get(back), seg)
+    maps = {k: B.empty(seg.shape, np.float32) for k in ("wm", "gm", "vt", "csf")}
+    h.split_segmentation(back, (6, 5, 7, 8), maps["wm"], maps["gm"], maps["vt"], maps["csf"])
+    ref = O.split_segmentation(seg, (6, 5, 7, 8), np.float32)
+    for k in maps:
+        assert np.array_equal(B.get(maps[k]), ref[k])
+    h.close()
