@@ -243,6 +243,8 @@ class Engine : public EngineBase {
     if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_V2")) use_v2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_L2WIN")) use_window = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_PDL")) use_pdl = std::atoi(e) != 0;
+    if (use_v2) use_pdl = false;  // the packed sweeps (sweeps_v2.cuh) carry no pdl_wait()
     max_window = rt::max_policy_window(device);
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
@@ -395,6 +397,20 @@ class Engine : public EngineBase {
     prof.after(slot, s);
     ++launches;
   }
+  // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
+  // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
+  // Off while profiling: the bracketing events would serialise the launches anyway.
+  bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
+  template <class... KA, class... A>
+  void LP(const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
+#if defined(GLIA_SIMT_EMU)
+    L(tag, k, g, b, smem, s, args...);
+#else
+    if (!use_pdl || G > 1 || prof.on) return L(tag, k, g, b, smem, s, args...);
+    simt::launch_pdl(k, g, b, smem, s, args...);
+    ++launches;
+#endif
+  }
   // the same with `win` (one field) marked streaming for L2 in this launch; no-op for fields beyond the
   // device's window limit (512^3: nothing fits in L2 anyway) or when GLIA_RD_L2WIN=0
   size_t max_window = 0;
@@ -403,6 +419,7 @@ class Engine : public EngineBase {
   void LS(const void* win, const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
     const size_t bytes = sizeof(T) * (size_t)nreal;
     const bool ok = use_window && GLIA_L2_HINTS && win && bytes <= max_window;
+    if (!ok) return LP(tag, k, g, b, smem, s, args...);
     const int slot = prof.before(tag, s);
     simt::launch_streaming(ok ? win : nullptr, bytes, k, g, b, smem, s, args...);
     prof.after(slot, s);
@@ -443,16 +460,16 @@ class Engine : public EngineBase {
       // register budget: 3-4 resident CTAs only pay for the 256-thread single-precision shapes
       const bool small = sizeof(T) == 4 && N <= 256;
       if (small && z_minb == 4)
-        L(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
           lines_z(), x, kfield, acc, (const C*)tw[2], done);
       else if (small && z_minb == 3)
-        L(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
           lines_z(), x, kfield, acc, (const C*)tw[2], done);
       else if (sizeof(T) == 4 && (z_minb == 2 || (z_minb512 == 2 && N == 512)))
-        L(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x,
+        LP(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x,
           kfield, acc, (const C*)tw[2], done);
       else
-        L(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x, kfield, acc,
+        LP(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x, kfield, acc,
           (const C*)tw[2], done);
     });
   }
@@ -543,14 +560,14 @@ class Engine : public EngineBase {
     const TileS ty = tile_y(), tx = tile_x();
     int nblk = 0;
     if (wv) {
-      GLIA_DISPATCH_N(n[2], L("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], LP("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done));
     } else {
-      GLIA_DISPATCH_N(n[2], L("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
+      GLIA_DISPATCH_N(n[2], LP("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
                                          (const C*)tw[2], done));
     }
-    GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], LP("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
     if (G > 1) {
       const TileX txd = tile_xd();
@@ -571,18 +588,18 @@ class Engine : public EngineBase {
       GLIA_DISPATCH_N(n[0], {
         if (use_pipe && pipe_fits<T, N>()) {
           const int ntiles = tx.nchunk * tx.n_outer;
-          L("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+          LP("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
             rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
         } else {
           L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat, (const C*)tw[0], sym, n[1], done);
         }
       });
     }
-    GLIA_DISPATCH_N(n[1], L("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
+    GLIA_DISPATCH_N(n[1], LP("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
                                        (const C*)shat, shat, (const C*)tw[1], done));
     GLIA_DISPATCH_N(n[2], {
       nblk = (int)grid_z<N>().x;
-      L(zout ? (want_rz ? "kz_c2r.rz" : "kz_c2r") : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
+      LP(zout ? (want_rz ? "kz_c2r.rz" : "kz_c2r") : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
                    zout, want_rz ? (const T*)rin : (const T*)nullptr, pp, (const C*)tw[2], done);
     });
     return nblk;
@@ -711,12 +728,12 @@ class Engine : public EngineBase {
     const int* done = iscal + I_DONE;
     const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
     const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
-    L("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal, comm,
+    LP("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal, comm,
       G > 1 ? next_epoch() : 0u, rseq++);
     const int nb2 = pc_apply(r, w, z, true, part(1), done);
-    L("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
+    LP("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
       comm, G > 1 ? next_epoch() : 0u, rseq++);
-    L("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
+    LP("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
                  (const int*)iscal, it);
   }
 

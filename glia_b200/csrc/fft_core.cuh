@@ -109,6 +109,18 @@ __device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) {
 }
 #endif
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may
+// become resident while its predecessor's last CTAs are still running; it does its set-up (indices,
+// twiddle registers from the constant per-axis table) and then waits here until the predecessor grid
+// has completed and its memory is visible.  Nothing produced by an earlier kernel may be touched
+// before this call.
+__device__ __forceinline__ void pdl_wait() {
+#if !defined(GLIA_SIMT_EMU)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the NEXT kernel's CTAs fill our tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // software prefetch of one 128-byte line into L1 (for operands an epilogue reads long after the
 // kernel starts: zero registers held across the transform)
 template <typename V>

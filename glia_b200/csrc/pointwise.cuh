@@ -105,6 +105,7 @@ static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, i
 template <typename T>
 __global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal, Comm comm, unsigned epoch,
                             unsigned seq) {
+  pdl_wait();
   if (iscal[I_DONE]) return;
   double d[1];
   sum_partials<1>(ppw, n, d);
@@ -116,6 +117,7 @@ __global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal, 
 template <typename T>
 __global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, int maxit, double dtol, Comm comm,
                            unsigned epoch, unsigned seq) {
+  pdl_wait();
   if (iscal[I_DONE]) return;
   double rz[2];
   sum_partials<2>(prz, n, rz);
@@ -130,6 +132,7 @@ __global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, i
 template <typename T>
 __global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const double* scal, const int* iscal,
                             int it) {
+  pdl_wait();
   if (it > iscal[I_ITS]) return;
   const T a = (T)scal[S_A], b = (T)scal[S_B];
   const int done = iscal[I_DONE];

@@ -47,6 +47,35 @@ inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStr
   }
   k<<<grid, block, smem, st>>>(static_cast<KA>(args)...);
 }
+inline void opt_in_smem(const void* k, size_t smem) {
+  if (smem <= 32 * 1024) return;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  auto& m = smem_attr_cache();
+  auto it = m.find(k);
+  if (it == m.end() || it->second < smem) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    m[k] = smem;
+  }
+}
+// programmatic dependent launch: the kernel may become resident (and run everything above its
+// pdl_wait()) while the previous kernel of the stream drains.  Only for kernels that call pdl_wait()
+// before touching anything an earlier kernel wrote, and before writing anything one reads.
+template <class... KA, class... A>
+inline void launch_pdl(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  opt_in_smem((const void*)k, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, static_cast<KA>(args)...);
+}
 // the same launch with an access-policy window: every access of this kernel into [win, win + bytes)
 // is treated as streaming (evict-first) by L2.  Used for operands that LDGSTS stages (cp.async
 // carries no usable per-instruction policy on sm_100a with this toolchain).

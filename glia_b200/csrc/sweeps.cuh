@@ -262,12 +262,13 @@ __global__ void __launch_bounds__(SL* (N / FftPlan<N>::E))
 ks_c2c(TileS geo, const cplx<T>* in, cplx<T>* out, const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   using F = LineFft<T, N>;
   constexpr int E = F::E;
-  if (done && *done) return;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
   const int l = threadIdx.x & (SL - 1), t = threadIdx.x / SL;
   typename F::Tw tw;
   F::load_twiddles(tw, twt, t);
+  pdl_wait();  // everything above is independent of earlier kernels
+  if (done && *done) return;
   const int outer = blockIdx.x / geo.nchunk, chunk = blockIdx.x % geo.nchunk;
   const long base = (long)blockIdx.y * geo.batch_stride + (long)outer * geo.outer_stride + (long)chunk * SL + l;
   cplx<T> v[E];
@@ -392,12 +393,13 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
           const int* __restrict__ done) {
   using F = LineFft<T, N>;
   constexpr int E = F::E;
-  if (done && *done) return;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
+  pdl_wait();  // everything above is independent of earlier kernels
+  if (done && *done) return;
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   cplx<T> v[E], kk[E];
@@ -544,12 +546,13 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   using F = LineFft<T, N>;
   constexpr int E = F::E;
-  if (done && *done) return;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
+  pdl_wait();  // everything above is independent of earlier kernels
+  if (done && *done) return;
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   T aa = (T)0;
@@ -609,12 +612,13 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   using F = LineFft<T, N>;
   constexpr int E = F::E;
-  if (done && *done) return;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
+  pdl_wait();  // everything above is independent of earlier kernels
+  if (done && *done) return;
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   const long oa = z.pair * 2 * (N / 2), ob = oa + N / 2;
