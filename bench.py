@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-3 gradient / Hessian / Phi timings")
+    ap.add_argument("--no-base", action="store_true", help="slab workload: skip the 1-GPU run of the same grid")
     ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     a = ap.parse_args()
@@ -590,9 +591,42 @@ def run_slab(a):
         "roofline": roofline,
         "kernels": kern,
     }
+    h.close()
+    barrier()
+    if rank == 0 and not a.no_base:
+        # the SAME global grid on ONE GPU (rank 0's, the slab handle released), in the same run: the
+        # denominator of the strong-scaling speed-up.  The driver's N = 1 line is the 256^3 headline
+        # workload, so this series carries its own 1-GPU point.
+        put = lambda x: torch.from_numpy(x).to(dev)
+        wm1, gm1, csf1, c01 = put(src["wm"]), put(src["gm"]), put(src["csf"]), put(src["c0"])
+        d11, cT1, p01 = torch.empty_like(c01), torch.empty_like(c01), torch.empty_like(c01)
+        h1 = RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt)
+        h1.resize_history(a.nt, a.dt)
+        h1.set_diffusion_tissue(wm1, gm1, csf1, 0.025, 0.0, 0.0, fsum)
+        h1.set_reaction_tissue(wm1, gm1, csf1, 10.0, 0.0, 0.0)
+        h1.prec_factor()
+        h1.solve_state(c01, d11, 0)
+        h1.set_diffusion_tissue(wm1, gm1, csf1, a.kappa, 0.0, 0.0, fsum)
+        h1.set_reaction_tissue(wm1, gm1, csf1, a.rho, 0.0, 0.0)
+        h1.prec_factor()
+        h1.forward_adjoint(c01, d11, cT1, p01)
+        nb = max(1, min(2, a.steps))
+        torch.cuda.synchronize()
+        h1.timer_start()
+        for _ in range(nb):
+            ks1, ka1 = h1.forward_adjoint(c01, d11, cT1, p01)
+        ms1 = h1.timer_stop_ms()
+        v1 = a.nt * nb / (ms1 * 1e-3)
+        line["strong_scaling_base"] = {
+            "n_gpus": 1, "value": v1, "unit": UNIT, "steps": nb, "ms_per_step": ms1 / nb,
+            "pcg_iterations": {"state": ks1, "adjoint": ka1},
+            "same_iterations_as_slab_run": bool((ks1, ka1) == (ks, ka)),
+            "speedup": value / v1, "note": "same global grid and inputs on rank 0's GPU alone, timed after the "
+            "slab run in this process"}
+        h1.close()
+    barrier()
     if rank == 0:
         print(json.dumps(line), flush=True)
-    h.close()
     dist.destroy_process_group()
 
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     "glia_rd_set_secondary_k": (_I, [_P, _P]),
     "glia_rd_set_reaction": (_I, [_P, _P]),
     "glia_rd_set_reaction_tissue": (_I, [_P, _P, _P, _P, _D, _D, _D]),
+    "glia_rd_update_reac_diff": (_I, [_P, _P, _P, _P, _P, _D, _D, _D, _D]),
     "glia_rd_apply_D": (_I, [_P, _P, _P, _I]),
     "glia_rd_prec_factor": (_I, [_P]),
     "glia_rd_diffusion_solve": (_I, [_P, _P, _D, C.POINTER(_I)]),

@@ -126,6 +126,10 @@ int glia_rd_set_reaction_tissue(glia_rd_t* h, const void* wm, const void* gm, co
                                 double rglm) {
   return guarded(h, [&](EngineBase& E) { E.v_set_reaction_tissue(wm, gm, csf, rs, rgm, rglm); });
 }
+int glia_rd_update_reac_diff(glia_rd_t* h, const void* bg, const void* gm, const void* vt, const void* csf,
+                             double rho_scale, double k_scale, double gm_r_scale, double gm_k_scale) {
+  return guarded(h, [&](EngineBase& E) { E.v_update_reac_diff(bg, gm, vt, csf, rho_scale, k_scale, gm_r_scale, gm_k_scale); });
+}
 int glia_rd_apply_D(glia_rd_t* h, void* dc, const void* c, int secondary) {
   return guarded(h, [&](EngineBase& E) { E.v_apply_D(dc, c, secondary); });
 }

@@ -244,6 +244,8 @@ class Engine : public EngineBase {
     if (const char* e = std::getenv("GLIA_RD_V2")) use_v2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_L2WIN")) use_window = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_PDL")) use_pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_C2C_PIPE")) use_c2c_pipe = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_PDL_SLAB")) use_pdl_slab = std::atoi(e) != 0;
     if (use_v2) use_pdl = false;  // the packed sweeps (sweeps_v2.cuh) carry no pdl_wait()
     max_window = rt::max_policy_window(device);
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
@@ -400,13 +402,18 @@ class Engine : public EngineBase {
   // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
   // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
   // Off while profiling: the bracketing events would serialise the launches anyway.
+  bool use_c2c_pipe = false;  // GLIA_RD_C2C_PIPE=1: persistent pipelined form of the preconditioner's y sweeps
   bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
+  // slab handles: only the rank-local chains (z, y sweeps, scalar kernels, vector update) overlap; the
+  // peer x sweeps and the k_peer_barrier launches around them go through L() and stay fully serialised,
+  // and a kernel launched without the attribute waits for the complete predecessor whatever it triggered.
+  bool use_pdl_slab = false;  // GLIA_RD_PDL_SLAB=1
   template <class... KA, class... A>
   void LP(const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
 #if defined(GLIA_SIMT_EMU)
     L(tag, k, g, b, smem, s, args...);
 #else
-    if (!use_pdl || G > 1 || prof.on) return L(tag, k, g, b, smem, s, args...);
+    if (!use_pdl || (G > 1 && !use_pdl_slab) || prof.on) return L(tag, k, g, b, smem, s, args...);
     simt::launch_pdl(k, g, b, smem, s, args...);
     ++launches;
 #endif
@@ -567,8 +574,16 @@ class Engine : public EngineBase {
                                          lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
                                          (const C*)tw[2], done));
     }
-    GLIA_DISPATCH_N(n[1], LP("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
-                                       (const C*)shat, shat, (const C*)tw[1], done));
+    GLIA_DISPATCH_N(n[1], {
+      if (use_c2c_pipe && use_pipe && pipe_fits<T, N>()) {
+        const int ntiles = ty.nchunk * ty.n_outer;
+        LP("ks_c2c.y", ks_c2c_pipe<T, N, -1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
+      } else {
+        LP("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
+           (const C*)tw[1], done);
+      }
+    });
     if (G > 1) {
       const TileX txd = tile_xd();
       const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
@@ -595,8 +610,16 @@ class Engine : public EngineBase {
         }
       });
     }
-    GLIA_DISPATCH_N(n[1], LP("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty,
-                                       (const C*)shat, shat, (const C*)tw[1], done));
+    GLIA_DISPATCH_N(n[1], {
+      if (use_c2c_pipe && use_pipe && pipe_fits<T, N>()) {
+        const int ntiles = ty.nchunk * ty.n_outer;
+        LP("ks_c2c.y", ks_c2c_pipe<T, N, +1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
+      } else {
+        LP("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
+           (const C*)tw[1], done);
+      }
+    });
     GLIA_DISPATCH_N(n[2], {
       nblk = (int)grid_z<N>().x;
       LP(zout ? (want_rz ? "kz_c2r.rz" : "kz_c2r") : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
@@ -697,6 +720,16 @@ class Engine : public EngineBase {
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_gm, gm, (T)0, (const T*)nullptr);
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_wm, wm, (T)1, (const T*)rho);
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_glm, csf, (T)1, (const T*)rho);
+    sync();
+  }
+  // mass-effect style refresh of rho(x) and k(x) between time steps.  Like the reference it leaves the
+  // averages k-bar (and with them the next prec_factor() symbol) and k_scale untouched:
+  // updateReacAndDiffCoefficients writes kxx_ only, kxx_avg_ keeps the value of the last setValues.
+  void update_reac_diff(const T* bg, const T* gm, const T* vt, const T* csf, double rho_s, double k_s, double gm_r,
+                        double gm_k) {
+    L("k_update_reac_diff", k_update_reac_diff<T>, grid_pw(nreal), dim3(256), 0, st, nreal, rho, kf, bg, gm, vt, csf,
+      (T)rho_s, (T)k_s, (T)gm_r, (T)gm_k);
+    if (G > 1) build_pencil(kf, kT);
     sync();
   }
   void apply_D(T* dc, const T* c, bool secondary) {
@@ -1267,6 +1300,10 @@ class Engine : public EngineBase {
   void v_set_reaction_tissue(const void* wm, const void* gm, const void* csf, double rs, double rgm,
                              double rglm) override {
     set_reaction_tissue((const T*)wm, (const T*)gm, (const T*)csf, rs, rgm, rglm);
+  }
+  void v_update_reac_diff(const void* bg, const void* gm, const void* vt, const void* csf, double rho_s, double k_s,
+                          double gm_r, double gm_k) override {
+    update_reac_diff((const T*)bg, (const T*)gm, (const T*)vt, (const T*)csf, rho_s, k_s, gm_r, gm_k);
   }
   void v_apply_D(void* dc, const void* c, int secondary) override { apply_D((T*)dc, (const T*)c, secondary != 0); }
   void v_prec_factor() override { prec_factor(); }

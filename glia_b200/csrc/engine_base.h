@@ -30,6 +30,8 @@ class EngineBase {
   virtual void v_set_reaction(const void* rho) = 0;
   virtual void v_set_reaction_tissue(const void* wm, const void* gm, const void* csf, double rs, double rgm,
                                      double rglm) = 0;
+  virtual void v_update_reac_diff(const void* bg, const void* gm, const void* vt, const void* csf, double rho_s,
+                                  double k_s, double gm_r, double gm_k) = 0;
   virtual void v_apply_D(void* dc, const void* c, int secondary) = 0;
   virtual void v_prec_factor() = 0;
   virtual int v_diffusion_solve(void* c, double dt) = 0;

@@ -190,6 +190,25 @@ __global__ void k_incr_avg(long n, T* t, const T* __restrict__ ci, const T* __re
   }
 }
 
+// PdeOperatorsMassEffect::updateReacAndDiffCoefficients (src/pde/PdeOperatorsMassEffect.cpp:98-138):
+// the per-time-step coefficient refresh of the mass-effect models, one pass for both fields.
+//   rho = rho_s * max(0, 1 - (bg + gm_r*gm + vt + csf)),  k = k_s * max(0, 1 - (bg + gm_k*gm + vt + csf))
+// (sum order as written there; kyy, kzz are copies of kxx, i.e. the same isotropic field here).
+template <typename T>
+__global__ void k_update_reac_diff(long n, T* rho, T* k, const T* __restrict__ bg, const T* __restrict__ gm,
+                                   const T* __restrict__ vt, const T* __restrict__ csf, T rho_s, T k_s, T gm_r, T gm_k) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T b = bg[i], g = gm[i], v = vt[i], c = csf[i];
+    T t = (T)1 - (((b + gm_r * g) + v) + c);
+    t = (t < (T)0) ? (T)0 : t;
+    rho[i] = t * rho_s;
+    t = (T)1 - (((b + gm_k * g) + v) + c);
+    t = (t < (T)0) ? (T)0 : t;
+    k[i] = t * k_s;
+  }
+}
+
 // out = a*x + b*y (y may be null)
 template <typename T>
 __global__ void k_axpby(long n, T* out, T a, const T* x, T b, const T* y) {

@@ -137,6 +137,11 @@ class RDHandle:
         self._ck(self.lib.glia_rd_set_reaction_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(rho_scale),
                                                       float(r_gm_wm), float(r_glm_wm)))
 
+    def update_reac_diff(self, bg, gm, vt, csf, rho_scale, k_scale, gm_r_scale, gm_k_scale):
+        """PdeOperatorsMassEffect::updateReacAndDiffCoefficients (src/pde/PdeOperatorsMassEffect.cpp:98-138)."""
+        self._ck(self.lib.glia_rd_update_reac_diff(self._h, _ptr(bg), _ptr(gm), _ptr(vt), _ptr(csf), float(rho_scale),
+                                                   float(k_scale), float(gm_r_scale), float(gm_k_scale)))
+
     def apply_D(self, dc, c, secondary=False):
         self._ck(self.lib.glia_rd_apply_D(self._h, _ptr(dc), _ptr(c), int(bool(secondary))))
 

@@ -96,6 +96,17 @@ int glia_rd_set_secondary_k(glia_rd_t* h, const void* ktilde);
 int glia_rd_set_reaction(glia_rd_t* h, const void* rho);
 int glia_rd_set_reaction_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf,
                                 double rho_scale, double r_gm_wm, double r_glm_wm);
+/* PdeOperatorsMassEffect::updateReacAndDiffCoefficients (src/pde/PdeOperatorsMassEffect.cpp:98-138),
+ * the coefficient refresh the mass-effect models do before every time step:
+ *   rho = rho_scale * max(0, 1 - (bg + gm_r_scale*gm + vt + csf)),
+ *   k   = k_scale   * max(0, 1 - (bg + gm_k_scale*gm + vt + csf)),
+ * gm_r_scale = 1 - r_gm_wm_ratio, gm_k_scale = 1 - k_gm_wm_ratio.  One pass, both fields written
+ * inside the handle.  As in the reference the averages k-bar used by glia_rd_prec_factor are NOT
+ * recomputed (they keep the value of the last glia_rd_set_diffusion[_tissue]); the time step is then
+ * glia_rd_prec_factor, [advection, not in this library], glia_rd_diffusion_solve(c, dt),
+ * glia_rd_reaction(c, NULL, dt) -- PdeOperatorsMassEffect.cpp:578-631. */
+int glia_rd_update_reac_diff(glia_rd_t* h, const void* bg, const void* gm, const void* vt, const void* csf,
+                             double rho_scale, double k_scale, double gm_r_scale, double gm_k_scale);
 /* DiffCoef::applyD / applyDWithSecondaryCoeffs (DiffCoef.cpp:249-300); dc may alias c. */
 int glia_rd_apply_D(glia_rd_t* h, void* dc, const void* c, int secondary);
 

@@ -301,6 +301,13 @@ class PdeOperatorsRD {
     if (linearized) c_lin = c_(iter);
     return glia_rd_reaction(spec_ops_->handle(), tumor_->c_t_.array(), c_lin, params_->dt);
   }
+  // PdeOperatorsMassEffect::updateReacAndDiffCoefficients(seg, tumor)  (PdeOperatorsMassEffect.cpp:98-138):
+  // the per-step coefficient refresh of models 4/5; bg/gm/vt/csf are the CURRENT (advected) maps.
+  ErrorCode updateReacAndDiffCoefficients(const Vec<Real>& bg, const Vec<Real>& gm, const Vec<Real>& vt,
+                                          const Vec<Real>& csf) {
+    return glia_rd_update_reac_diff(spec_ops_->handle(), bg.array(), gm.array(), vt.array(), csf.array(), params_->rho,
+                                    params_->k, 1.0 - params_->r_gm_wm_ratio, 1.0 - params_->k_gm_wm_ratio);
+  }
   const Real* c_(int i) { return hist(GLIA_HIST_C, i); }
   const Real* p_(int i) { return hist(GLIA_HIST_P, i); }
   const Real* c_half_(int i) { return hist(GLIA_HIST_C_HALF, i); }

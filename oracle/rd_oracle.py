@@ -245,6 +245,37 @@ def reac_coef(rho_scale, r_gm_wm, r_glm_wm, wm, gm, csf):
     return rho.astype(wm.dtype)
 
 
+def update_reac_diff_mass_effect(bg, gm, vt, csf, rho_scale, k_scale, gm_r_scale, gm_k_scale):
+    """PdeOperatorsMassEffect::updateReacAndDiffCoefficients, CPU branch
+    (src/pde/PdeOperatorsMassEffect.cpp:116-123): returns (rho, kxx).  The averages
+    kxx_avg_ are NOT touched there -- the caller keeps its DiffCoef's old ones."""
+    t = bg.dtype.type
+    tmp = (t(1) - (((bg + t(gm_r_scale) * gm) + vt) + csf)).astype(bg.dtype)
+    rho = (np.where(tmp < 0, t(0), tmp) * t(rho_scale)).astype(bg.dtype)
+    tmp = (t(1) - (((bg + t(gm_k_scale) * gm) + vt) + csf)).astype(bg.dtype)
+    kxx = (np.where(tmp < 0, t(0), tmp) * t(k_scale)).astype(bg.dtype)
+    return rho, kxx
+
+
+def mass_effect_rd_steps(c0, tissue_seq, k: "DiffCoef", solver: "DiffusionSolver", rho_scale, k_scale,
+                         gm_r_scale, gm_k_scale, dt):
+    """The reaction-diffusion part of PdeOperatorsMassEffect::solveState's time loop
+    (src/pde/PdeOperatorsMassEffect.cpp:578-631): per step refresh rho, k from the
+    current tissue maps; precFactor(); [advection -- not restated: `tissue_seq[i]` is
+    the (bg, gm, vt, csf) the step sees]; diff_solver_->solve(c, dt) with the FULL dt;
+    reaction(0, i) with the full dt (order-1 splitting).  Returns (c, [ksp its])."""
+    c = c0.copy()
+    its = []
+    for bg, gm, vt, csf in tissue_seq:
+        rho, kxx = update_reac_diff_mass_effect(bg, gm, vt, csf, rho_scale, k_scale, gm_r_scale, gm_k_scale)
+        k.kxx = kxx
+        solver.prec_factor()
+        c = solver.solve(c, dt)
+        its.append(solver.ksp_itr)
+        c = reaction_nonlinear(c, rho, dt)
+    return c, its
+
+
 # --------------------------------------------------------------------------
 # L2  DiffusionSolver  (Crank-Nicolson, PETSc-CG semantics)
 # --------------------------------------------------------------------------

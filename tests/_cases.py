@@ -249,6 +249,39 @@ def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_gr
     return res
 
 
+def case_mass_effect_steps(B, n, dtype, nsteps=3, dt=0.04):
+    """SURVEY 8f rank 4: the RD part of PdeOperatorsMassEffect::solveState's loop
+    (src/pde/PdeOperatorsMassEffect.cpp:578-631) -- coefficients refreshed from moving tissue maps
+    before every step, precFactor(), full-dt diffusion solve, full-dt reaction -- through the C ABI
+    against the oracle.  "Advection" is a rigid periodic shift of the maps by one voxel per step."""
+    sh = shape3(n)
+    P = make_problem(n, dtype)
+    t = np.dtype(dtype).type
+    bg = (1.0 - P["filt"]).astype(dtype)
+    vt = (0.3 * P["csf"]).astype(dtype)
+    seq = [tuple(np.roll(f, i, axis=i % 3).copy() for f in (bg, P["gm"], vt, P["csf"])) for i in range(nsteps)]
+    rho_s, k_s, gm_r, gm_k = 8.0, 0.05, 1.0 - 0.2, 1.0 - 0.1
+    k = O.DiffCoef(sh, dtype)
+    k.set_values(k_s, 0.1, 0.0, P["wm"], P["gm"], P["csf"], P["filt"])   # fixes k-bar once, like the ctor path
+    solver = O.DiffusionSolver(k, dt_ctx=dt)
+    c_ref, its_ref = O.mass_effect_rd_steps(P["c0"], seq, k, solver, rho_s, k_s, gm_r, gm_k, dt)
+
+    h = B.handle(n, dtype, dt_ctx=dt)
+    dev = {key: B.put(P[key]) for key in ("wm", "gm", "csf")}
+    h.set_diffusion_tissue(dev["wm"], dev["gm"], dev["csf"], k_s, 0.1, 0.0, float(P["filt"].sum(dtype=np.float64)))
+    c = B.put(P["c0"])
+    its = []
+    for fields in seq:
+        d = [B.put(f) for f in fields]
+        h.update_reac_diff(d[0], d[1], d[2], d[3], rho_s, k_s, gm_r, gm_k)
+        h.prec_factor()
+        its.append(h.diffusion_solve(c, dt))
+        h.reaction(c, None, dt)
+    out = B.get(c)
+    h.close()
+    return {"its": (its, its_ref), "c": rel(out, c_ref), "moved": rel(out, P["c0"])}
+
+
 def case_objective_hessian(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
     """evaluateObjectiveAndGradient + Gauss-Newton Hessian product (with diffusivity inversion,
     nk = 2) through the C ABI vs the oracle's DerivativeOperatorsRD, observation mask on."""

@@ -52,6 +52,14 @@ def test_forward_adjoint_gradient(B, dtype):
     assert r["grad"] < 10 * tol, r["grad_vals"]
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_mass_effect_style_steps(B, dtype):
+    r = Cs.case_mass_effect_steps(B, 32, dtype, nsteps=2)
+    assert r["its"][0] == r["its"][1], r
+    assert r["c"] < Cs.TOL[np.dtype(dtype)], r
+    assert r["moved"] > 1e-2
+
+
 @pytest.mark.parametrize("dtype", [np.float64])   # single precision of the same case runs on the GPU
 def test_objective_gradient_hessian(B, dtype):
     r = Cs.case_objective_hessian(B, 32, dtype, nt=1)

@@ -87,6 +87,16 @@ def test_objective_gradient_hessian(B, n, nt, dtype):
     assert r["h_y"] < 10 * tol and r["h_y_ponly"] < 10 * tol and r["h_k"] < 50 * tol, r
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n", [64, 128])
+def test_mass_effect_style_steps(B, n, dtype):
+    """k(x), rho(x) refreshed before every step, precFactor per step, order-1 splitting."""
+    r = Cs.case_mass_effect_steps(B, n, dtype, nsteps=3)
+    assert r["its"][0] == r["its"][1], r
+    assert r["c"] < Cs.TOL[np.dtype(dtype)], r
+    assert r["moved"] > 1e-2
+
+
 def test_adjoint_without_store(B):
     r = Cs.case_forward_adjoint(B, 64, np.float64, nt=2, dt=0.04, adjoint_store=False, with_grad=False)
     assert r["its_adj"][0] == r["its_adj"][1]

@@ -1,4 +1,4 @@
-"""CPU coverage of the N > 1 (slab-decomposed) path: world_size 2 (and 4), gloo rendezvous on
+"""CPU coverage of the N > 1 (slab-decomposed) path: world_size 2, 4 and 8, gloo rendezvous on
 127.0.0.1, the product sources compiled against the SIMT emulator, arenas in POSIX shared
 memory so that the ranks really read and write each other's fields and spin on each other's
 flags, exactly like the GPU ranks do over NVLink."""
@@ -9,7 +9,7 @@ import _cases as Cs
 import _slab
 
 
-@pytest.mark.parametrize("world,dtype", [(2, "float32"), (4, "float64")])
+@pytest.mark.parametrize("world,dtype", [(2, "float32"), (4, "float64"), (8, "float64")])
 def test_slab_operators(emu_lib, world, dtype):
     res = _slab.run(world, "emu", emu_lib, "operators", n=32, dtype=dtype)
     tol = 1e-12 if dtype == "float64" else 5e-6
