@@ -402,7 +402,7 @@ class Engine : public EngineBase {
   // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
   // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
   // Off while profiling: the bracketing events would serialise the launches anyway.
-  bool use_c2c_pipe = false;  // GLIA_RD_C2C_PIPE=1: persistent pipelined form of the preconditioner's y sweeps
+  bool use_c2c_pipe = true;  // GLIA_RD_C2C_PIPE=0: one-tile-per-CTA form of the preconditioner's y sweeps
   bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
   // slab handles: only the rank-local chains (z, y sweeps, scalar kernels, vector update) overlap; the
   // peer x sweeps and the k_peer_barrier launches around them go through L() and stay fully serialised,

@@ -110,16 +110,38 @@ __device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) {
 #endif
 
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may
-// become resident while its predecessor's last CTAs are still running; it does its set-up (indices,
+// be scheduled while its predecessor's last CTAs are still draining; it does its set-up (indices,
 // twiddle registers from the constant per-axis table) and then waits here until the predecessor grid
 // has completed and its memory is visible.  Nothing produced by an earlier kernel may be touched
 // before this call.
+#ifndef GLIA_PDL_MODE
+// 0: no PDL instructions (probe builds), 1: wait only, 2: explicit early trigger + wait.  Measured: the explicit
+// griddepcontrol.launch_dependents on entry slows the multi-wave z sweeps (kz_deriv2 600 -> 629 us, kz_r2c.axpy
+// 473 -> 530 us at 512^3) and gains nothing over the implicit trigger at CTA exit (90.0 vs 88.5 time-steps/s at
+// 256^3), so the default is the wait alone.
+#define GLIA_PDL_MODE 1
+#endif
 __device__ __forceinline__ void pdl_wait() {
-#if !defined(GLIA_SIMT_EMU)
+#if !defined(GLIA_SIMT_EMU) && GLIA_PDL_MODE >= 1
+#if GLIA_PDL_MODE >= 2
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the NEXT kernel's CTAs fill our tail
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
+
+// Where a sweep kernel waits for its predecessor and tests the PCG's `done` flag (written by an earlier
+// kernel, so only readable after the wait).  Measured on the B200 (gpurun_out/r1l_*, profiles/r1l_pdl_matrix.txt):
+// waiting AFTER the twiddle registers are loaded is the faster place for lines up to 256 points
+// (kz_r2c.axpy 45 vs 51 us at 256^3), but at 512 points it costs the z sweeps up to 45 % (kz_r2c.axpy
+// 473 vs 325 us at 512^3), so those wait first thing.  GLIA_PDL_TOP = 0 / 1 forces one place for probe builds.
+#ifndef GLIA_PDL_TOP
+#define GLIA_PDL_TOP (N >= 512)
+#endif
+#define GLIA_PDL_ENTRY_EARLY(done) \
+  if constexpr (GLIA_PDL_TOP) { pdl_wait(); if ((done) && *(done)) return; }
+#define GLIA_PDL_ENTRY_LATE(done) \
+  if constexpr (!(GLIA_PDL_TOP)) { pdl_wait(); if ((done) && *(done)) return; }
 
 // software prefetch of one 128-byte line into L1 (for operands an epilogue reads long after the
 // kernel starts: zero registers held across the transform)

@@ -260,6 +260,7 @@ ks_gradprod(TileS geo, const cplx<T>* __restrict__ c, const cplx<T>* __restrict_
 template <typename T, int N, int DIR>
 __global__ void __launch_bounds__(SL* (N / FftPlan<N>::E))
 ks_c2c(TileS geo, const cplx<T>* in, cplx<T>* out, const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+  GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
@@ -267,8 +268,7 @@ ks_c2c(TileS geo, const cplx<T>* in, cplx<T>* out, const cplx<T>* __restrict__ t
   const int l = threadIdx.x & (SL - 1), t = threadIdx.x / SL;
   typename F::Tw tw;
   F::load_twiddles(tw, twt, t);
-  pdl_wait();  // everything above is independent of earlier kernels
-  if (done && *done) return;
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
   const int outer = blockIdx.x / geo.nchunk, chunk = blockIdx.x % geo.nchunk;
   const long base = (long)blockIdx.y * geo.batch_stride + (long)outer * geo.outer_stride + (long)chunk * SL + l;
   cplx<T> v[E];
@@ -391,6 +391,7 @@ template <typename T, int N, int ADD = 0, int MINB = 1>
 __global__ void __launch_bounds__(zthreads<N>(), MINB)
 kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, const cplx<T>* __restrict__ twt,
           const int* __restrict__ done) {
+  GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
@@ -398,8 +399,7 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
-  pdl_wait();  // everything above is independent of earlier kernels
-  if (done && *done) return;
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   cplx<T> v[E], kk[E];
@@ -544,6 +544,7 @@ template <typename T, int N, int PRO>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal_a, cplx<T>* shat,
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+  GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
@@ -551,8 +552,7 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
-  pdl_wait();  // everything above is independent of earlier kernels
-  if (done && *done) return;
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   T aa = (T)0;
@@ -610,6 +610,7 @@ template <typename T, int N, int EPI>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict__ r, double* partial,
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+  GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
@@ -617,8 +618,7 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
   ZCtx<T, N> z(ln);
   typename F::Tw tw;
   F::load_twiddles(tw, twt, z.t);
-  pdl_wait();  // everything above is independent of earlier kernels
-  if (done && *done) return;
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   const long oa = z.pair * 2 * (N / 2), ob = oa + N / 2;
