@@ -631,6 +631,9 @@ def run_slab(a):
 
 
 def main():
+    # NCCL prints its version banner (NCCL_DEBUG=VERSION on the bench boxes) to stdout; the contract is ONE
+    # JSON line there, so send NCCL's own log to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     a = parse()
     if a.impl == "reference":
         run_reference(a)
