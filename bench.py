@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "rd256", "rd512", "slab512", "replicas"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "rd256", "rd512", "slab512", "replicas", "ensemble"],
                     help="auto: 1 GPU -> rd256 (BASELINE config[1]); N GPUs -> slab512 (config[3]: one 512^3 grid "
                          "cut into N x-slabs, strong scaling). rd512 = the same 512^3 solve on one GPU (the strong-"
                          "scaling base). replicas = N independent rd256 solves (weak).")
@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-3 gradient / Hessian / Phi timings")
+    ap.add_argument("--members", type=int, default=64, help="ensemble workload: number of members (<= 64)")
+    ap.add_argument("--concurrency", type=int, default=4, help="ensemble workload: members in flight per GPU")
     ap.add_argument("--no-base", action="store_true", help="slab workload: skip the 1-GPU run of the same grid")
     ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
@@ -69,7 +71,7 @@ def parse():
         a.workload = "rd256" if max(world, a.gpus) == 1 else "slab512"
     big = a.workload in ("rd512", "slab512")
     if a.n is None:
-        a.n = 512 if big else 256
+        a.n = 512 if big else (128 if a.workload == "ensemble" else 256)
     if a.nt is None:
         a.nt = 10 if big else 25      # config 4 uses nt = 10, config 2 nt = 25
     if a.dt is None:
@@ -630,6 +632,124 @@ def run_slab(a):
     dist.destroy_process_group()
 
 
+def run_ensemble(a):
+    """Config 5 of BASELINE.json: 64 independent 128^3 forward solves, (kappa, rho) on an 8 x 8 grid
+    (kappa in [0.005, 0.05] log-spaced, rho in [4, 15]), spread over the ranks (8 per GPU at
+    N = 8), `--concurrency` members in flight per GPU -- one handle (= one stream) each, driven from
+    host threads (ctypes releases the GIL inside the library).  Replicas only: no collective on the
+    data path; the value is aggregate member-time-steps per second."""
+    import threading
+    import torch
+    from glia_b200.rd import RDHandle
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    atlas, c0, dtype = make_inputs(a)
+    put = lambda x: torch.from_numpy(x).to(dev)
+    wm, gm, csf, c0d = put(atlas["wm"]), put(atlas["gm"]), put(atlas["csf"]), put(c0)
+    fsum = float(atlas["filter"].astype(np.float64).sum())
+    kappas = np.exp(np.linspace(np.log(0.005), np.log(0.05), 8))
+    rhos = np.linspace(4.0, 15.0, 8)
+    members = [(float(k), float(r)) for k in kappas for r in rhos][: a.members]
+    mine = members[rank::world]
+    conc = max(1, min(a.concurrency, len(mine)))
+    handles = [RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt) for _ in range(conc)]
+    outs = [torch.empty_like(c0d) for _ in range(conc)]
+    for h in handles:
+        h.resize_history(a.nt, a.dt)
+    torch.cuda.synchronize()
+    its_total = [0] * conc
+    ms_thread = [0.0] * conc
+
+    def worker(j, timed):
+        torch.cuda.set_device(local)
+        h = handles[j]
+        its = 0
+        if timed:
+            h.timer_start()
+        for kappa, rho in mine[j::conc]:
+            h.set_diffusion_tissue(wm, gm, csf, kappa, 0.0, 0.0, fsum)
+            h.set_reaction_tissue(wm, gm, csf, rho, 0.0, 0.0)
+            h.prec_factor()
+            its += h.solve_state(c0d, outs[j], 0)
+        if timed:
+            ms_thread[j] = h.timer_stop_ms()
+        its_total[j] = its
+
+    def sweep(timed):
+        th = [threading.Thread(target=worker, args=(j, timed)) for j in range(conc)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    for _ in range(a.warmup):
+        sweep(False)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = sum(h.launch_count for h in handles)
+    ms = 0.0
+    for _ in range(a.steps):
+        sweep(True)
+        ms += max(ms_thread)     # the streams start together; the slowest one ends the step
+    barrier()
+    launches = sum(h.launch_count for h in handles) - l0
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    value = len(members) * a.nt * a.steps / (ms * 1e-3)
+    nsolves = 2 * a.nt * len(mine)
+    F = float(np.dtype(dtype).itemsize) * a.n ** 3
+    peak, peak_src = peaks()
+    model_bytes = step_bytes_model(F, sum(its_total), nsolves, a.nt * len(mine)) - 7.0 * F * a.nt * len(mine)
+    line = {
+        "metric": "rd_ensemble_member_time_steps_per_sec", "value": value, "unit": "member-time-steps/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": f"config 5: {len(members)} independent {a.n}^3 RD forward solves, (kappa, rho) on an "
+                               "8 x 8 grid, replicas only (no data-path collective)", "n": a.n, "nt": a.nt,
+                   "dt": a.dt, "members": len(members), "members_per_gpu": len(mine), "concurrency_per_gpu": conc,
+                   "l2": "a 128^3 field is 8 MB: the working set of a member lives in the 126 MB L2 by design; "
+                         "consecutive members use different coefficients, nothing is reused across timed steps "
+                         "except the tissue maps"},
+        "pcg_iterations": {"state": int(sum(its_total)), "solves": nsolves,
+                           "mean_per_solve": sum(its_total) / max(nsolves, 1)},
+        "gpu_launches": int(launches) * world, "clocks": clocks,
+        "roofline": {"bound": "hbm", "whole_step": {"alg_bytes_per_gpu": model_bytes,
+                                                     "achieved": model_bytes * a.steps / (ms * 1e-3) / 1e9,
+                                                     "frac": model_bytes * a.steps / (ms * 1e-3) / 1e9 / peak},
+                     "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                     "note": "forward only: A_min model F*[sum_solves(33+30 m_i) + 3 nt] per member; at 128^3 the "
+                             "path is launch- and latency-bound, not HBM-bound"},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for h in handles:
+        h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     # NCCL prints its version banner (NCCL_DEBUG=VERSION on the bench boxes) to stdout; the contract is ONE
     # JSON line there, so send NCCL's own log to stderr
@@ -639,6 +759,8 @@ def main():
         run_reference(a)
     elif a.workload == "slab512":
         run_slab(a)
+    elif a.workload == "ensemble":
+        run_ensemble(a)
     else:
         run_b200(a)
 
