@@ -62,7 +62,34 @@ inline size_t max_policy_window(int device) {
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) != cudaSuccess || v < 0) { cudaGetLastError(); v = 0; }
   return (size_t)v;
 }
-inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+// the handle's stream gets the highest priority so that, when a side stream (below) has work in flight,
+// CTAs of the main stream's kernels are placed first on SMs as they free up
+inline int stream_create(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); least = greatest = 0; }
+  return (int)cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);
+}
+// fork / join of a lowest-priority side stream by events (no host synchronisation)
+struct Fork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int create() {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); least = 0; }
+    int e = (int)cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least);
+    if (e) return e;
+    if ((e = (int)cudaEventCreateWithFlags(&fork, cudaEventDisableTiming))) return e;
+    return (int)cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+  }
+  void destroy() {
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    if (side) cudaStreamDestroy(side);
+    fork = join = nullptr; side = nullptr;
+  }
+  void begin(cudaStream_t main) { cudaEventRecord(fork, main); cudaStreamWaitEvent(side, fork, 0); }
+  void end(cudaStream_t main) { cudaEventRecord(join, side); cudaStreamWaitEvent(main, join, 0); }
+};
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 // per-launch CUDA-event profiler (off by default: zero overhead besides one branch)
@@ -180,6 +207,17 @@ class Engine : public EngineBase {
   int z_minb = 1;        // resident CTAs per SM the z second-derivative sweep is compiled for (GLIA_RD_ZMINB: 1, 3, 4).
                          // Measured at 256^3 f32: 1 (123 registers, no cap) 49.6 us; 3 / 4 (80 / 64 registers) 82 us
   int z_minb512 = 1;     // the same for 512-point z lines (168 registers uncapped = 1 CTA/SM; 2 caps at 128)
+  // slab D-apply: run the rank-local z sweep on a side stream (into acc2) WHILE the peer x sweep, which is
+  // NVLink-bound and leaves SM time unused, runs on a share of the SMs; the y sweep then takes acc + acc2
+  // (the same two addends the serial order sums, so the result is bit-identical).  GLIA_RD_XZ=0/1.
+  // Measured at 2 GPUs, 512^3 (gpurun_out/r1q_*): 9.17 time-steps/s serial, 9.48 with the x sweep on 55 % of the
+  // SMs, 9.60 on 74 %.
+  bool use_xz = true;
+  int xz_ctas = 0;       // CTAs of the x sweep while overlapped (GLIA_RD_XZ_CTAS; 0 = 75 % of the persistent grid)
+  rt::Fork fork;
+  T* acc2 = nullptr;
+  T* z_out_override = nullptr;
+  bool z_side = false, pdl_hold = false;
   int dist_debug = 0;    // GLIA_RD_DIST_DEBUG: timing experiments only (results are WRONG): 1 = x sweeps read
                          // local rows instead of peer rows, 2 = write local rows instead of peer rows
 
@@ -251,6 +289,10 @@ class Engine : public EngineBase {
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_ZMINB512")) z_minb512 = std::atoi(e);
+    if (const char* e = std::getenv("GLIA_RD_XZ")) use_xz = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_XZ_CTAS")) xz_ctas = std::atoi(e);
+    if (G == 1 || !use_pipe || use_v2 || (sizeof(T) == 8 && (n[0] > 256 || n[1] > 256))) use_xz = false;
+    if (use_xz) GLIA_CHECK(fork.create());
     timer.create();
     nreal = (long)n0l * n[1] * n[2];
     ncplx = nreal / 2;
@@ -258,6 +300,7 @@ class Engine : public EngineBase {
     dt_ctx = (T)dt_ctx_;
     std::vector<T**> fields = {&kf, &ktil, &rho, &b, &r, &z, &p, &w, &acc, &c_t, &p_0, &work11, &Tk, &Tr};
     if (G > 1) { fields.push_back(&kT); fields.push_back(&ktilT); fields.push_back(&stage); fields.push_back(&TkX); }
+    if (use_xz) fields.push_back(&acc2);  // same switch on every rank: the arenas keep one layout
     const size_t fbytes = sizeof(T) * nreal;  // a multiple of 256 bytes for every admissible grid
     const size_t comm_bytes = 4096;
     arena_bytes = fbytes * (fields.size() + 1) + comm_bytes;
@@ -312,6 +355,7 @@ class Engine : public EngineBase {
     rt::dev_free(phi_filter); rt::dev_free(phi_dots);
     timer.destroy();
     prof.destroy();
+    fork.destroy();
     rt::stream_destroy(st);
   }
 
@@ -413,7 +457,7 @@ class Engine : public EngineBase {
 #if defined(GLIA_SIMT_EMU)
     L(tag, k, g, b, smem, s, args...);
 #else
-    if (!use_pdl || (G > 1 && !use_pdl_slab) || prof.on) return L(tag, k, g, b, smem, s, args...);
+    if (!use_pdl || (G > 1 && !use_pdl_slab) || prof.on || pdl_hold) return L(tag, k, g, b, smem, s, args...);
     simt::launch_pdl(k, g, b, smem, s, args...);
     ++launches;
 #endif
@@ -463,20 +507,22 @@ class Engine : public EngineBase {
   // z sweep of the D-apply: acc (+)= D_z(k D_z x)
   template <int ADD>
   void sweep_deriv2_z(const char* tag, const T* x, const T* kfield, const int* done) {
+    T* const zo = z_out_override ? z_out_override : acc;
+    const cudaStream_t zs = z_side ? fork.side : st;
     GLIA_DISPATCH_N(n[2], {
       // register budget: 3-4 resident CTAs only pay for the 256-thread single-precision shapes
       const bool small = sizeof(T) == 4 && N <= 256;
       if (small && z_minb == 4)
-        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-          lines_z(), x, kfield, acc, (const C*)tw[2], done);
+        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs,
+          lines_z(), x, kfield, zo, (const C*)tw[2], done);
       else if (small && z_minb == 3)
-        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-          lines_z(), x, kfield, acc, (const C*)tw[2], done);
+        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs,
+          lines_z(), x, kfield, zo, (const C*)tw[2], done);
       else if (sizeof(T) == 4 && (z_minb == 2 || (z_minb512 == 2 && N == 512)))
-        LP(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x,
-          kfield, acc, (const C*)tw[2], done);
+        LP(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs, lines_z(), x,
+          kfield, zo, (const C*)tw[2], done);
       else
-        LP(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), x, kfield, acc,
+        LP(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs, lines_z(), x, kfield, zo,
           (const C*)tw[2], done);
     });
   }
@@ -490,7 +536,7 @@ class Engine : public EngineBase {
   // one S-geometry D(k D x) sweep on local rows; returns the number of partial-sum blocks
   template <int EPI>
   int sweep_deriv2_local(int nline, const char* tag, const TileS& g, const T* x, const T* kfield, T alpha, T* out1,
-                         T* out2, double* pp, const int* done) {
+                         T* out2, double* pp, const int* done, const T* acc_extra = nullptr) {
     constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
     int nblk = 0;
     if constexpr (std::is_same<T, float>::value) {
@@ -511,6 +557,15 @@ class Engine : public EngineBase {
         const int ntiles = g.nchunk * g.n_outer;
         const dim3 gr = grid_pipe<N>(ntiles);
         nblk = (int)gr.x;
+        if constexpr (EPI != EPI_ADD && EPI != EPI_SET) {
+          if (acc_extra) {
+            const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk};
+            LS(x, tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
+               st, ntiles, rows_s(g, x), rows_s(g, kfield), a2, rows_s(g, out1), rows_s(g, out2),
+               (const C*)tw_for(nline, g), alpha, pp, done);
+            return nblk;
+          }
+        }
         LS(x, tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
           ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2), (const C*)tw_for(nline, g),
           alpha, pp, done);
@@ -533,12 +588,25 @@ class Engine : public EngineBase {
     const TileX txd = tile_xd();
     const TileS ty = tile_y();
     const PeerRows<T> xr = rows(x, 1), ar = rows(acc, 2);
+    const bool overlapped = use_xz && !prof.on;
+    if (overlapped) {
+      // acc2 = D_z(k D_z x) on the side stream, concurrently with the barriers and the peer x sweep
+      fork.begin(st);
+      z_side = true; z_out_override = acc2; pdl_hold = true;
+      sweep_deriv2_z<0>("kz_deriv2.side", x, kfield, done);
+      z_side = false; z_out_override = nullptr; pdl_hold = false;
+    }
     barrier();
     GLIA_DISPATCH_N(n[0], {
       if (use_pipe && pipe_fits<T, N>()) {
         const int ntiles = txd.nchunk * txd.n_outer;
         const RowsX<T> rx{xr, txd}, ra{ar, txd};
-        L("kx_deriv2_dist", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, grid_pipe<N>(ntiles),
+        dim3 gx = grid_pipe<N>(ntiles);
+        if (overlapped) {  // leave SMs to the z sweep
+          const int cap = xz_ctas > 0 ? xz_ctas : (int)(0.75 * nsm * pipe_ctas<T, N>());
+          if ((int)gx.x > cap) gx.x = (unsigned)(cap < 1 ? 1 : cap);
+        }
+        L("kx_deriv2_dist", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, gx,
           block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)const_cast<T*>(kpen), txd}, ra, ra, ra,
           (const C*)tw[0], (T)0, (double*)nullptr, done);
       } else {
@@ -547,9 +615,10 @@ class Engine : public EngineBase {
       }
     });
     barrier();
-    sweep_deriv2_z<1>("kz_deriv2.add", x, kfield, done);
+    if (overlapped) fork.end(st);
+    else sweep_deriv2_z<1>("kz_deriv2.add", x, kfield, done);
     const char* ytag = EPI == EPI_MATVEC ? "ks_deriv2.y.matvec" : (EPI == EPI_RHS ? "ks_deriv2.y.rhs" : "ks_deriv2.y.epi");
-    return sweep_deriv2_local<EPI>(n[1], ytag, ty, x, kfield, alpha, out1, out2, pp, done);
+    return sweep_deriv2_local<EPI>(n[1], ytag, ty, x, kfield, alpha, out1, out2, pp, done, overlapped ? acc2 : nullptr);
   }
 
   template <int EPI>

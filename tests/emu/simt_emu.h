@@ -174,9 +174,18 @@ inline void ipc_free(void* p, size_t n, const unsigned char* handle) {
 inline int sm_count(int) { return 3; }
 inline size_t max_policy_window(int) { return 0; }
 inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
+// fork / join of a side stream: the emulator runs every launch to completion in program order
+struct Fork {
+  cudaStream_t side = 0;
+  int create() { return 0; }
+  void destroy() {}
+  void begin(cudaStream_t) {}
+  void end(cudaStream_t) {}
+};
 inline void stream_destroy(cudaStream_t) {}
 inline const char* err_string(int) { return "emu"; }
 struct Profiler {
+  bool on = false;
   int before(const char*, cudaStream_t) { return -1; }
   void after(int, cudaStream_t) {}
   void begin() {}
