@@ -249,6 +249,53 @@ def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_gr
     return res
 
 
+def case_pcg_edges(B, n, dtype):
+    """Edge behaviour of DiffusionSolver::solve as the reference has it: k_scale == 0 returns at once
+    (DiffusionSolver.cpp:227); a zero field converges at the iteration-0 test; a capped maxit stops
+    after exactly that many iterations with the iterate PETSc would hold; a loose rtol needs fewer
+    iterations than the default and still matches the oracle run with the same tolerance."""
+    sh = shape3(n)
+    P = make_problem(n, dtype)
+    res = {}
+    # (1) k_scale == 0
+    h = B.handle(n, dtype, dt_ctx=0.04)
+    kd = B.put(P["k"].kxx)
+    h.set_diffusion(kd, [float(P["k"].kxx_avg)] * 3, 0.0)
+    h.prec_factor()
+    c = B.put(P["c0"])
+    res["kscale0_its"] = h.diffusion_solve(c, 0.02)
+    res["kscale0_unchanged"] = bool(np.array_equal(B.get(c), P["c0"]))
+    h.close()
+    # (2) zero field, (3) maxit, (4) loose rtol
+    h, dev = setup_handle(B, P, n, dtype, nt=1, dt=0.04)
+    zf = B.put(np.zeros(sh, dtype))
+    res["zero_its"] = h.diffusion_solve(zf, 0.02)
+    res["zero_out"] = float(np.abs(B.get(zf)).max())
+    solver = O.DiffusionSolver(P["k"], dt_ctx=0.04)
+    solver.prec_factor()
+    full = solver.solve(P["c0"], 0.02)
+    full_its = solver.ksp_itr
+    cap = max(1, full_its - 1)
+    solver2 = O.DiffusionSolver(P["k"], dt_ctx=0.04)
+    solver2.prec_factor()
+    solver2.MAXIT = cap
+    capped = solver2.solve(P["c0"], 0.02)
+    h.set_ksp_tolerances(maxit=cap)
+    c = B.put(P["c0"])
+    res["maxit"] = (h.diffusion_solve(c, 0.02), solver2.ksp_itr, cap)
+    res["maxit_err"] = rel(B.get(c), capped)
+    solver3 = O.DiffusionSolver(P["k"], dt_ctx=0.04)
+    solver3.prec_factor()
+    solver3.RTOL = 1e-2
+    loose = solver3.solve(P["c0"], 0.02)
+    h.set_ksp_tolerances(rtol=1e-2)
+    c = B.put(P["c0"])
+    res["loose"] = (h.diffusion_solve(c, 0.02), solver3.ksp_itr, full_its)
+    res["loose_err"] = rel(B.get(c), loose)
+    h.close()
+    return res
+
+
 def case_mass_effect_steps(B, n, dtype, nsteps=3, dt=0.04):
     """SURVEY 8f rank 4: the RD part of PdeOperatorsMassEffect::solveState's loop
     (src/pde/PdeOperatorsMassEffect.cpp:578-631) -- coefficients refreshed from moving tissue maps

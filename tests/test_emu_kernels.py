@@ -53,6 +53,17 @@ def test_forward_adjoint_gradient(B, dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
+def test_pcg_edge_cases(B, dtype):
+    r = Cs.case_pcg_edges(B, 32, dtype)
+    assert r["kscale0_its"] == 0 and r["kscale0_unchanged"], r
+    assert r["zero_its"] == 0 and r["zero_out"] == 0.0, r
+    assert r["maxit"][0] == r["maxit"][1] == r["maxit"][2], r
+    assert r["maxit_err"] < Cs.TOL[np.dtype(dtype)], r
+    assert r["loose"][0] == r["loose"][1] and r["loose"][0] <= r["loose"][2], r
+    assert r["loose_err"] < Cs.TOL[np.dtype(dtype)], r
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_mass_effect_style_steps(B, dtype):
     r = Cs.case_mass_effect_steps(B, 32, dtype, nsteps=2)
     assert r["its"][0] == r["its"][1], r
