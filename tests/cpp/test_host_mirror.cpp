@@ -114,6 +114,26 @@ void applying_phi() {
   REQUIRE(cmax <= 0.7 * (1 + 1e-5) && cmax > 0.3);
 }
 
+// models 4/5 time-loop body (src/pde/PdeOperatorsMassEffect.cpp:578-631) as a maintainer would write it over the
+// mirror: coefficient refresh from the current maps, precFactor, full-dt diffusion, full-dt reaction.  Compiled
+// here (so the mirror's signature is checked on every build); the parity case itself is
+// tests/test_gpu_parity.py::test_mass_effect_style_steps through the same C entry point.
+template <typename Real>
+int mass_effect_rd_step(PdeOperatorsRD<Real>& pde, DiffusionSolver<Real>& diff_solver, Tumor<Real>& tumor,
+                        const Vec<Real>& bg, const Vec<Real>& gm, const Vec<Real>& vt, const Vec<Real>& csf,
+                        const Parameters& params, int i) {
+  int ierr = pde.updateReacAndDiffCoefficients(bg, gm, vt, csf);
+  if (ierr) return ierr;
+  if ((ierr = diff_solver.precFactor())) return ierr;
+  if ((ierr = diff_solver.solve(tumor.c_t_, params.dt))) return ierr;
+  return pde.reaction(0, i);
+}
+template int mass_effect_rd_step<float>(PdeOperatorsRD<float>&, DiffusionSolver<float>&, Tumor<float>&, const Vec<float>&,
+                                        const Vec<float>&, const Vec<float>&, const Vec<float>&, const Parameters&, int);
+template int mass_effect_rd_step<double>(PdeOperatorsRD<double>&, DiffusionSolver<double>&, Tumor<double>&,
+                                         const Vec<double>&, const Vec<double>&, const Vec<double>&, const Vec<double>&,
+                                         const Parameters&, int);
+
 int main() {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("no CUDA device\n"); return 77; }
