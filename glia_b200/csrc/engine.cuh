@@ -16,6 +16,7 @@
 #include "sweeps.cuh"
 #include "sweeps_dist.cuh"
 #include "sweeps_pipe.cuh"
+#include "sweeps_zpipe.cuh"
 #include "sweeps_v2.cuh"
 
 namespace glia {
@@ -282,6 +283,7 @@ class Engine : public EngineBase {
     if (const char* e = std::getenv("GLIA_RD_V2")) use_v2 = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_L2WIN")) use_window = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_PDL")) use_pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GLIA_RD_ZPIPE")) use_zpipe = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_C2C_PIPE")) use_c2c_pipe = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_PDL_SLAB")) use_pdl_slab = std::atoi(e) != 0;
     if (use_v2) use_pdl = false;  // the packed sweeps (sweeps_v2.cuh) carry no pdl_wait()
@@ -446,6 +448,7 @@ class Engine : public EngineBase {
   // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
   // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
   // Off while profiling: the bracketing events would serialise the launches anyway.
+  bool use_zpipe = false;  // GLIA_RD_ZPIPE=1: persistent warp-private pipelined z second-derivative sweep (unmeasured)
   bool use_c2c_pipe = true;  // GLIA_RD_C2C_PIPE=0: one-tile-per-CTA form of the preconditioner's y sweeps
   bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
   // slab handles: only the rank-local chains (z, y sweeps, scalar kernels, vector update) overlap; the
@@ -509,6 +512,20 @@ class Engine : public EngineBase {
   void sweep_deriv2_z(const char* tag, const T* x, const T* kfield, const int* done) {
     T* const zo = z_out_override ? z_out_override : acc;
     const cudaStream_t zs = z_side ? fork.side : st;
+    if (use_zpipe) {  // round-2 candidate, see sweeps_zpipe.cuh
+      bool launched = false;
+      GLIA_DISPATCH_N(n[2], {
+        if (zpipe_fits<T, N>()) {
+          const long np = lines_z().npairs;
+          const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());
+          const int cap = nsm * zpipe_ctas<T, N>();
+          LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(ngroups < cap ? ngroups : cap)), dim3(zthreads<N>()),
+             zpipe_smem<T, N>(), zs, lines_z(), ngroups, x, kfield, zo, (const C*)tw[2], done);
+          launched = true;
+        }
+      });
+      if (launched) return;
+    }
     GLIA_DISPATCH_N(n[2], {
       // register budget: 3-4 resident CTAs only pay for the 256-thread single-precision shapes
       const bool small = sizeof(T) == 4 && N <= 256;

@@ -1,0 +1,121 @@
+// sweeps_zpipe.cuh -- persistent, warp-private, LDGSTS-pipelined form of the z second-derivative
+// sweep (kz_deriv2, sweeps.cuh).  ROUND-2 CANDIDATE: correct on the emulator and through the C ABI,
+// NOT yet measured on a B200, therefore off by default (GLIA_RD_ZPIPE=1 selects it).
+//
+// Why: kz_deriv2 puts the 64 scalar loads of a line pair's x and k in flight at once; at 512-point
+// lines that costs 168 registers = ONE 256-thread CTA per SM (8 warps) and 41 % of the copy peak
+// (DESIGN.md 6, next lever 1).  Here the x lines of the NEXT line-pair group ride into shared
+// memory on cp.async while the current group is transformed, k is sent towards L1 on entry of the
+// round and read at the point of use, and nothing but the 16 complex values of the transform lives
+// across it.  A line pair belongs to N/E <= 32 threads of one warp, which fetch exactly the bytes
+// they later read, so the whole pipeline needs __syncwarp only: no CTA barrier, warps drift freely.
+//
+//   smem per line pair = stage[0] | stage[1] (2N reals each) | exchange (zpad complex)
+#pragma once
+#include "sweeps_pipe.cuh"
+
+namespace glia {
+
+template <typename T, int N>
+__host__ __device__ constexpr size_t zpipe_pair_bytes() {
+  return 2 * (size_t)(2 * N) * sizeof(T) + (size_t)zpad<N>() * sizeof(cplx<T>);
+}
+template <typename T, int N>
+__host__ __device__ constexpr size_t zpipe_smem() { return zlines<N>() * zpipe_pair_bytes<T, N>(); }
+template <typename T, int N>
+__host__ __device__ constexpr bool zpipe_fits() {
+  return (N / FftPlan<N>::E) <= 32 && zpipe_smem<T, N>() <= 200 * 1024;
+}
+template <typename T, int N>
+__host__ __device__ constexpr int zpipe_ctas() {
+  const int c = (int)((224 * 1024) / zpipe_smem<T, N>());
+  return c < 1 ? 1 : (c > 2 ? 2 : c);
+}
+
+// acc (+)= D_z(k D_z x) over `ngroups` groups of zlines<N>() line pairs; CTA b takes groups b, b + gridDim.x, ...
+template <typename T, int N, int ADD>
+__global__ void __launch_bounds__(zthreads<N>(), zpipe_ctas<T, N>())
+kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restrict__ kf, T* acc,
+               const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+  GLIA_PDL_ENTRY_EARLY(done);
+  using F = LineFft<T, N>;
+  constexpr int E = F::E, TPL = F::TPL, LPC = zlines<N>();
+  static_assert(TPL <= 32, "a line pair must live inside one warp");
+  GLIA_DYN_SMEM(smraw);
+  const int t = threadIdx.x % TPL, lp = threadIdx.x / TPL;
+  // this pair's private shared memory: two stages of 2N reals, then the exchange region
+  unsigned char* mine = smraw + (size_t)lp * zpipe_pair_bytes<T, N>();
+  T* stage0 = reinterpret_cast<T*>(mine);
+  cplx<T>* sm = reinterpret_cast<cplx<T>*>(mine + 2 * (size_t)(2 * N) * sizeof(T));
+  typename F::Tw tw;
+  F::load_twiddles(tw, twt, t);
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
+  SyncWarp sy;
+  const AmZ am{0};  // `sm` already points at this pair's region
+  constexpr int CH = (2 * N * (int)sizeof(T)) / 16;  // 16-byte chunks of one pair's two lines
+  static_assert(CH % TPL == 0, "chunks per thread");
+
+  auto pair_of = [&](int group) -> long {
+    long p = (long)group * LPC + lp;
+    return p < ln.npairs ? p : ln.npairs - 1;  // ragged tail: re-do the last pair, stores predicated
+  };
+  auto prefetch = [&](T* stage, int group) {
+    const char* src = reinterpret_cast<const char*>(x + pair_of(group) * 2 * N);
+    GLIA_UNROLL
+    for (int i = 0; i < CH / TPL; ++i) {
+      const int c = t + i * TPL;
+      cp_async16(reinterpret_cast<char*>(stage) + 16 * c, src + 16 * c);
+    }
+  };
+
+  int group = blockIdx.x, s = 0;
+  if (group < ngroups) prefetch(stage0, group);
+  cp_async_commit();
+  for (; group < ngroups; group += gridDim.x, s ^= 1) {
+    T* st = stage0 + (size_t)s * (2 * N);
+    const int next = group + gridDim.x;
+    if (next < ngroups) prefetch(stage0 + (size_t)(s ^ 1) * (2 * N), next);
+    cp_async_commit();
+    const long pair = pair_of(group);
+    const bool active = (long)group * LPC + lp < ln.npairs;
+    const long la = pair * 2 * N, lb = la + N;
+    {  // k (and the accumulator of the ADD form) towards L1: read after the first / second derivative
+      constexpr int PER = 128 / (int)sizeof(T);
+      for (int i = t; i < 2 * N / PER; i += TPL) {
+        prefetch_l1(kf + la + i * PER);
+        if (ADD) prefetch_l1(acc + la + i * PER);
+      }
+    }
+    cp_async_wait<1>();
+    sy();  // the copies of the other lanes of this pair are visible too
+    cplx<T> v[E];
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+      v[e] = {st[pos], st[N + pos]};
+    }
+    deriv_inplace<T, N>(v, tw, sm, am, sy, t);
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+      v[e].x *= kf[la + pos];
+      v[e].y *= kf[lb + pos];
+    }
+    deriv_inplace<T, N>(v, tw, sm, am, sy, t);
+    if (active) {
+      GLIA_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+        cplx<T> o = v[e];
+        if (ADD) { o.x += acc[la + pos]; o.y += acc[lb + pos]; }
+        acc[la + pos] = o.x;
+        acc[lb + pos] = o.y;
+      }
+    }
+    // this round's reads of stage s precede the transforms' __syncwarp()s, so the prefetch the next
+    // round issues into it cannot overtake them
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace glia

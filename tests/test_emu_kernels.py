@@ -96,3 +96,17 @@ def test_phi_apply_and_transpose(B, dtype):
     e_apply, e_t, e_adj, zero_ok = Cs.case_phi(B, 32, dtype)
     tol = Cs.TOL[np.dtype(dtype)]
     assert e_apply < tol and e_t < tol and e_adj < 10 * tol and zero_ok
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_zpipe_candidate_is_equivalent(B, dtype, monkeypatch):
+    """The round-2 candidate kz_deriv2_pipe (GLIA_RD_ZPIPE=1, sweeps_zpipe.cuh) computes exactly what the
+    default z second-derivative sweep does, three-pass 512-point lines included."""
+    for n in ([(32, 32, 512)] if np.dtype(dtype) == np.float32 else [(32, 64, 64)]):
+        monkeypatch.delenv("GLIA_RD_ZPIPE", raising=False)
+        ref = Cs.case_apply_D(B, n, dtype, sinusoidal=False)
+        monkeypatch.setenv("GLIA_RD_ZPIPE", "1")
+        got = Cs.case_apply_D(B, n, dtype, sinusoidal=False)
+        monkeypatch.delenv("GLIA_RD_ZPIPE", raising=False)
+        assert got == ref, (n, got, ref)
+
