@@ -154,6 +154,28 @@ __device__ __forceinline__ void prefetch_l1(const V* p) {
 #endif
 }
 
+#ifndef GLIA_TW_LDG
+#define GLIA_TW_LDG 0
+#endif
+// read-only load of a twiddle-table entry; volatile, because a plain __ldg is hoisted out of the transforms by
+// ptxas and the values sit in registers again
+template <typename T>
+__device__ __forceinline__ cplx<T> ld_table(const cplx<T>* p) {
+#if defined(GLIA_SIMT_EMU)
+  return *p;
+#else
+  if constexpr (sizeof(T) == 4) {
+    float x, y;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
+    return {(T)x, (T)y};
+  } else {
+    double x, y;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+    return {(T)x, (T)y};
+  }
+#endif
+}
+
 // ---------------------------------------------------------------- plans ----
 template <int N> struct FftPlan;
 template <> struct FftPlan<32>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 4,  R2 = 1; };
@@ -300,7 +322,17 @@ struct LineFft {
     return n;
   }
   static constexpr int NTW = ntw() > 0 ? ntw() : 1;
-  struct Tw { cplx<T> w[NTW]; };
+  // GLIA_TW_LDG (probe builds, default 0): three-pass plans (512-point lines) hold 28 complex inter-pass
+  // twiddles per thread.  Level 1 reads the pass-0 twiddles from the 4 KB per-axis table at the point of use
+  // (read-only path, L1-resident) instead of keeping them in registers; level 2 does so for every pass.
+  // Same table entries either way, so results are bit-identical.  ptxas evidence in DESIGN.md 6 (lever 1).
+  static constexpr int TWL = (P == 3) ? GLIA_TW_LDG : 0;
+  __host__ __device__ static constexpr bool tw_in_regs(int p) { return TWL == 0 || (TWL == 1 && p >= 1); }
+  struct Tw {
+    cplx<T> w[NTW];
+    const cplx<T>* table;
+    int t;
+  };
 
   // location (natural position index at pass 0) of register (g, a) of pass p for thread t
   template <int p>
@@ -323,6 +355,8 @@ struct LineFft {
 
   // table[j] = exp(-2 pi i j / N), j < N (built on the host in double)
   __device__ static __forceinline__ void load_twiddles(Tw& tw, const cplx<T>* __restrict__ table, int t) {
+    tw.table = table;
+    tw.t = t;
     int idx = 0;
     GLIA_UNROLL
     for (int p = 0; p + 1 < P; ++p) {
@@ -330,7 +364,10 @@ struct LineFft {
       for (int g = 0; g < Gp(p); ++g) {
         const int b = (t + TPL * g) % Mp(p);
         GLIA_UNROLL
-        for (int c = 1; c < R(p); ++c) tw.w[idx++] = table[(b * c * (N / Np(p))) % N];
+        for (int c = 1; c < R(p); ++c) {
+          if (tw_in_regs(p)) tw.w[idx] = table[(b * c * (N / Np(p))) % N];
+          ++idx;
+        }
       }
     }
   }
@@ -352,7 +389,13 @@ struct LineFft {
       for (int g = 0; g < Gp(p); ++g) {
         GLIA_UNROLL
         for (int c = 1; c < R(p); ++c) {
-          const cplx<T> w = tw.w[twoff(p) + g * (R(p) - 1) + (c - 1)];
+          cplx<T> w;
+          if constexpr (tw_in_regs(p)) {
+            w = tw.w[twoff(p) + g * (R(p) - 1) + (c - 1)];
+          } else {
+            const int b = (tw.t + TPL * g) % Mp(p);
+            w = ld_table(tw.table + (b * c * (N / Np(p))) % N);
+          }
           v[g * R(p) + c] = CONJ ? cmulc(v[g * R(p) + c], w) : cmul(v[g * R(p) + c], w);
         }
       }
