@@ -392,6 +392,9 @@ def run_b200(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world),
         "pcg_iterations": {"state": ks, "adjoint": ka, "solves": nsolves, "mean_per_solve": (ks + ka) / nsolves},
+        "notes": {"xz_overlap": os.environ.get("GLIA_RD_XZ", "1") != "0",
+                  "kernels": "per-kernel times come from a separate event-bracketed pass, which runs the serial order "
+                             "(no x||z overlap, no programmatic dependent launch); the timed region uses both"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * F), "d2h_bytes_per_step": int(2 * F),
                 "ms_per_step": ms_e2e / a.steps, "matches_device_path": e2e_ok},
         "gpu_launches": int(launches),
