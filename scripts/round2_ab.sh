@@ -11,7 +11,6 @@ L=$PWD/glia_b200/lib
 run() { tag=$1; shift
   env "$@" $B --steps 3 --warmup 3 > gpurun_out/r2ab_256_$tag.json 2>> gpurun_out/r2ab.err
   env "$@" $B --workload rd512 --steps 1 --warmup 1 > gpurun_out/r2ab_512_$tag.json 2>> gpurun_out/r2ab.err; }
-GLIA_RD_ZPIPE=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "apply_D or forward_adjoint or K1" 2>&1 | tail -2
 run base GLIA_RD_ZPIPE=0
 run zpipe GLIA_RD_ZPIPE=1
 for v in tw1 tw2; do

@@ -32,9 +32,9 @@ def test_slab_operators_gpu(cuda_lib, dtype):
     for world in _worlds():
         res = _slab.run(world, "cuda", cuda_lib, "operators", n=128, dtype=dtype)
         tol = 1e-11 if dtype == "float64" else 5e-6
-        for r in res:
-            assert max(r["grad"]) < tol and r["div"] < tol, (world, r)
-            assert r["applyD"] <= max(r["applyD_budget"], tol), (world, r)
+        # global relative L2 of the distributed fields (root-sum-square of the ranks' shares)
+        assert max(_slab.combine(res, "grad")) < tol and _slab.combine(res, "div") < tol, (world, res)
+        assert _slab.combine(res, "applyD") <= max(res[0]["applyD_budget"], tol), (world, res)
 
 
 @pytest.mark.parametrize("n,nt,dtype", [(64, 3, "float64"), (128, 3, "float32"), (256, 2, "float32")])
@@ -46,7 +46,7 @@ def test_slab_forward_adjoint_gradient_gpu(cuda_lib, n, nt, dtype):
         tol = Cs.TOL[np.dtype(dtype)]
         for r in res:
             assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], (world, r)
-            assert r["cT"] < tol and r["p0"] < tol, (world, r)
             assert r["grad"] < 20 * tol, (world, r)
-            assert r["fa_cT"] < tol and r["fa_p0"] < tol, (world, r)
+        for key in ("cT", "p0", "fa_cT", "fa_p0"):   # global relative L2 (north_star's measure)
+            assert _slab.combine(res, key) < tol, (world, key, res)
         assert len({tuple(r["fa_its"]) for r in res}) == 1
