@@ -19,8 +19,18 @@ between barriers, max over ranks.
             the CPU restatement of the reference path (oracle/rd_oracle_torch.py: reference
             operation order, all host threads) on a bounded sample of the same workload
 
-N > 1 (torchrun, one rank per GPU): independent replicas of the same solve, no data-path
-collective ("scaling": "weak"); the slab-decomposed single solve is described in DESIGN.md.
+  parity    (inside `config`, so that the driver's record keeps it) the GPU path against the CPU
+            restatement on the cpu_baseline sample itself: same k, rho, c0, d1, nt -- relative L2 of
+            c(T) and p(0) and the PCG iteration counts of both
+  cufft_baseline
+            the reference's own CUDA call sequence (cuFFT 3-D R2C/C2R through torch.fft + unfused
+            elementwise kernels + host dot read-backs, scripts/cufft_compare.py) on the same GPU in the
+            same run -- comparison only, nothing in glia_b200 calls cuFFT
+
+N > 1 (torchrun, one rank per GPU): ONE 512^3 grid cut into N x-slabs (BASELINE config[3], "scaling":
+"strong"); the line carries its own 1-GPU point of the same grid (`config.strong_scaling_base`) and the
+slab result's relative L2 against that 1-GPU solve (`config.parity`).  `--workload replicas` runs N
+independent 256^3 solves instead ("weak").
 """
 from __future__ import annotations
 
@@ -63,7 +73,8 @@ def parse():
     ap.add_argument("--members", type=int, default=64, help="ensemble workload: number of members (<= 64)")
     ap.add_argument("--concurrency", type=int, default=4, help="ensemble workload: members in flight per GPU")
     ap.add_argument("--no-base", action="store_true", help="slab workload: skip the 1-GPU run of the same grid")
-    ap.add_argument("--ref-nt", type=int, default=1, help="time steps per reference-arm sample")
+    ap.add_argument("--ref-nt", type=int, default=None,
+                    help="time steps per CPU sample (default: 3 for --impl reference, 1 for the in-line cpu_baseline)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -76,6 +87,8 @@ def parse():
         a.nt = 10 if big else 25      # config 4 uses nt = 10, config 2 nt = 25
     if a.dt is None:
         a.dt = 1.0 / a.nt
+    if a.ref_nt is None:
+        a.ref_nt = (3 if a.n <= 256 else 1) if a.impl == "reference" else 1
     return a
 
 
@@ -224,12 +237,18 @@ def cpu_reference_sample(a, atlas, c0, nt_sample):
     c0t = torch.from_numpy(c0).to(tdt)
     d1 = (0.9 * c0t).contiguous()
 
+    keep = {}
+
     def run():
-        cT, p0, pde = OT.forward_adjoint(k, kavg, a.kappa, rho, c0t, d1, nt_sample, a.dt)
+        # dt_ctx = dt/2: the GPU arm's precFactor() runs after an earlier solve has left the context at dt/2
+        # (trap T2; in an inversion every gradient evaluation is in that state, DerivativeOperators.cpp:340)
+        cT, p0, pde = OT.forward_adjoint(k, kavg, a.kappa, rho, c0t, d1, nt_sample, a.dt, dt_ctx=a.dt / 2)
+        keep.update(cT=cT, p0=p0, ks=pde.ksp_state, ka=pde.ksp_adj, d1=d1)
         return pde.ksp_state + pde.ksp_adj
 
-    desc = (f"{nt_sample} forward+adjoint time step(s) at {a.n}^3 {a.precision}, restated reference CPU path "
-            f"(3-D FFT grad/div, 12 FFTs per PCG iteration, torch CPU FFT + elementwise, {cores} threads); "
+    run.keep = keep
+    desc = (f"the first {nt_sample} forward+adjoint time step(s) at {a.n}^3 {a.precision} (d1 = 0.9 c0), restated reference "
+            f"CPU path (3-D FFT grad/div, 12 FFTs per PCG iteration, torch CPU FFT + elementwise, {cores} threads); "
             f"no MPI/PETSc/AccFFT on this box")
     return run, cores, desc
 
@@ -268,11 +287,94 @@ def run_reference(a):
         "config": dict(workload_config(a, 1), time_steps_per_bench_step=a.ref_nt,
                        note="reference arm: each step is a bounded sample of the workload"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
-                         "pcg_iterations_per_sample": its},
+                         "pcg_iterations_per_sample": its, "pcg_iterations_per_solve": its / (4.0 * a.ref_nt),
+                         "note": "the first time steps are the stiffest (more PCG iterations per solve than the mean of "
+                                 "the full nt-step run the GPU arm times); compare per-iteration rates with "
+                                 "pcg_iterations_per_solve"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def gpu_parity_vs_cpu_sample(a, atlas, c0, keep, device, fsum):
+    """The GPU path on exactly the cpu_baseline sample (same k, rho, c0, d1, nt, same solver-context state):
+    relative L2 of c(T) and p(0) against the CPU restatement's fields and the PCG iteration counts of both."""
+    import torch
+    from glia_b200.rd import RDHandle
+    dev = torch.device("cuda", device)
+    put = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    h = RDHandle(a.n, a.precision, device=device, dt_ctx=a.dt / 2)
+    wm, gm, csf = put(atlas["wm"]), put(atlas["gm"]), put(atlas["csf"])
+    h.set_diffusion_tissue(wm, gm, csf, a.kappa, 0.0, 0.0, fsum)
+    h.set_reaction_tissue(wm, gm, csf, a.rho, 0.0, 0.0)
+    h.prec_factor()
+    h.resize_history(a.ref_nt, a.dt)
+    c0d = put(c0)
+    d1 = keep["d1"].numpy()
+    cT, p0 = torch.empty_like(c0d), torch.empty_like(c0d)
+    torch.cuda.synchronize()
+    ks, ka = h.forward_adjoint(c0d, put(d1), cT, p0)
+    out = {"what": f"GPU path vs the CPU restatement on the cpu_baseline sample ({a.ref_nt} time step(s) at {a.n}^3)",
+           "rel_l2_cT": rel_l2(cT.cpu().numpy(), keep["cT"].numpy()),
+           "rel_l2_p0": rel_l2(p0.cpu().numpy(), keep["p0"].numpy()),
+           "its_gpu": [int(ks), int(ka)], "its_oracle": [int(keep["ks"]), int(keep["ka"])],
+           "tolerance": 1e-5 if a.precision == "f32" else 1e-10}
+    out["ok"] = bool(out["rel_l2_cT"] < out["tolerance"] and out["rel_l2_p0"] < out["tolerance"]
+                     and out["its_gpu"] == out["its_oracle"])
+    h.close()
+    return out
+
+
+def cufft_baseline(a, atlas, c0, device, fsum, nt_sample=2):
+    """The reference's CUDA call sequence (3-D cuFFT R2C/C2R per gradient / divergence / preconditioner apply,
+    unfused elementwise kernels, host dot read-backs: src/grad/SpectralOperators.cpp:100-261,
+    src/mat/DiffCoef.cpp:206-271) on the same GPU -- comparison only."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("cufft_compare", os.path.join(ROOT, "scripts", "cufft_compare.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    dev = torch.device("cuda", device)
+    tdt = torch.float32 if a.precision == "f32" else torch.float64
+    wm = torch.from_numpy(atlas["wm"]).to(dev).to(tdt)
+    k, rho = a.kappa * wm, a.rho * wm
+    kavg = float(k.sum(dtype=torch.float64)) / fsum
+    c0d = torch.from_numpy(c0).to(dev).to(tdt)
+    d1 = 0.9 * c0d
+    path = mod.CufftPath(k, kavg, rho, a.dt, dev)
+    path.forward_adjoint(c0d, d1, 1)  # warm-up: cuFFT plans, allocator
+    path.nfft = path.its = 0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    path.forward_adjoint(c0d, d1, nt_sample)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    its, nfft = path.its, path.nfft
+    x = torch.randn(a.n, a.n, a.n, device=dev, dtype=tdt)
+    xh = torch.fft.rfftn(x)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        xh = torch.fft.rfftn(x)
+        x = torch.fft.irfftn(xh, s=x.shape, norm="forward")
+    e1.record()
+    torch.cuda.synchronize()
+    fft_ms = e0.elapsed_time(e1) / 20
+    del path, x, xh
+    torch.cuda.empty_cache()
+    return {"value": nt_sample / (ms * 1e-3), "unit": UNIT, "kind": "cuFFT call sequence of the reference's CUDA backend "
+            "(torch.fft on this GPU), comparison only", "sample": f"the first {nt_sample} forward+adjoint time steps at {a.n}^3",
+            "its_per_solve": its / (4.0 * nt_sample), "ffts": nfft, "cufft_ms_per_3d_fft": fft_ms,
+            "share_in_cufft": nfft * fft_ms / ms}
 
 
 # ---------------------------------------------------------------- GPU arm ----
@@ -392,7 +494,7 @@ def run_b200(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world),
         "pcg_iterations": {"state": ks, "adjoint": ka, "solves": nsolves, "mean_per_solve": (ks + ka) / nsolves},
-        "notes": {"xz_overlap": os.environ.get("GLIA_RD_XZ", "1") != "0",
+        "notes": {
                   "kernels": "per-kernel times come from a separate event-bracketed pass, which runs the serial order "
                              "(no x||z overlap, no programmatic dependent launch); the timed region uses both"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * F), "d2h_bytes_per_step": int(2 * F),
@@ -424,16 +526,39 @@ def run_b200(a):
         line["config3"] = {"objective_gradient_ms": t_grad, "objective_gradient_pcg_its": list(og["its"]),
                            "hessian_matvec_kappa_ms": t_hess, "hessian_matvec_pcg_its": list(hits),
                            "phi_apply_np8_ms": t_phi, "phi_apply_transpose_np8_ms": t_phit}
+    h.close()
+    mean_its = (ks + ka) / nsolves
+    line["config"]["pcg_iterations"] = line["pcg_iterations"]
+    line["config"]["whole_step_roofline_frac"] = roofline["whole_step"]["frac"]
+    if world == 1 and not a.no_extras:
+        try:
+            cb = cufft_baseline(a, atlas, c0, local, fsum)
+            # per PCG iteration the two do the same numerical work: normalise the sample's stiffer first steps
+            cb["value_at_gpu_arm_its_per_solve"] = cb["value"] * cb["its_per_solve"] / mean_its
+            cb["speedup_of_this_library"] = value / cb["value_at_gpu_arm_its_per_solve"]
+            line["cufft_baseline"] = cb
+            line["config"]["cufft_baseline"] = {k: cb[k] for k in ("value", "its_per_solve", "share_in_cufft",
+                                                                   "value_at_gpu_arm_its_per_solve", "speedup_of_this_library")}
+        except Exception as e:  # comparison only: never fail the bench line over it
+            line["cufft_baseline"] = {"unavailable": repr(e)[:200]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         run, cores, desc = cpu_reference_sample(a, atlas, c0, a.ref_nt)
         t0 = time.perf_counter()
         its = run()
         tc = time.perf_counter() - t0
+        cpu_ips = its / (4.0 * a.ref_nt)
         line["cpu_baseline"] = {"value": a.ref_nt / tc, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": desc, "seconds": tc, "pcg_iterations_per_sample": its}
+                                "sample": desc, "seconds": tc, "pcg_iterations_per_sample": its,
+                                "pcg_iterations_per_solve": cpu_ips,
+                                "value_at_gpu_arm_its_per_solve": a.ref_nt / tc * cpu_ips / mean_its}
+        par = gpu_parity_vs_cpu_sample(a, atlas, c0, run.keep, local, fsum)
+        line["parity"] = par
+        line["config"]["parity"] = par
+        if not par["ok"]:
+            print(json.dumps(line), flush=True)
+            raise SystemExit("PARITY FAILURE against the CPU restatement: " + json.dumps(par))
     if rank == 0:
         print(json.dumps(line), flush=True)
-    h.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -599,6 +724,16 @@ def run_slab(a):
     }
     h.close()
     barrier()
+    line["config"]["pcg_iterations"] = line["pcg_iterations"]
+    line["config"]["whole_step_roofline_frac_per_gpu"] = roofline["whole_step"]["frac"]
+    line["config"]["nvlink_frac_per_direction"] = roofline["nvlink"]["frac"]
+    # the slab result, gathered on rank 0, against the 1-GPU solve of the same grid below
+    slabs_cT = [torch.empty_like(cT) for _ in range(world)] if rank == 0 else None
+    slabs_p0 = [torch.empty_like(p0) for _ in range(world)] if rank == 0 else None
+    if not a.no_base:
+        dist.gather(cT, slabs_cT, dst=0)
+        dist.gather(p0, slabs_p0, dst=0)
+        torch.cuda.synchronize()
     if rank == 0 and not a.no_base:
         # the SAME global grid on ONE GPU (rank 0's, the slab handle released), in the same run: the
         # denominator of the strong-scaling speed-up.  The driver's N = 1 line is the 256^3 headline
@@ -627,12 +762,30 @@ def run_slab(a):
             "n_gpus": 1, "value": v1, "unit": UNIT, "steps": nb, "ms_per_step": ms1 / nb,
             "pcg_iterations": {"state": ks1, "adjoint": ka1},
             "same_iterations_as_slab_run": bool((ks1, ka1) == (ks, ka)),
-            "speedup": value / v1, "note": "same global grid and inputs on rank 0's GPU alone, timed after the "
-            "slab run in this process"}
+            "speedup": value / v1, "efficiency": value / v1 / world,
+            "note": "same global grid and inputs on rank 0's GPU alone, timed after the slab run in this process"}
         h1.close()
+        # parity of the slab-decomposed solve: global relative L2 against the 1-GPU solve of the same inputs
+        # (the 1-GPU path is the one the oracle parity tests and the N = 1 bench line's `parity` pin)
+        def gl2(slabs, full):
+            num = sum(float(((torch.cat([sl]).double() - full[r * lsh[0]:(r + 1) * lsh[0]].double()) ** 2).sum())
+                      for r, sl in enumerate(slabs))
+            return math.sqrt(num) / max(float(full.double().norm()), 1e-300)
+        tol = 1e-5 if a.precision == "f32" else 1e-10
+        par = {"what": f"{world}-slab solve vs the 1-GPU solve of the same {a.n}^3 inputs, global relative L2",
+               "rel_l2_cT": gl2(slabs_cT, cT1), "rel_l2_p0": gl2(slabs_p0, p01),
+               "its_slab": [int(ks), int(ka)], "its_1gpu": [int(ks1), int(ka1)], "tolerance": tol}
+        par["ok"] = bool(par["rel_l2_cT"] < tol and par["rel_l2_p0"] < tol and par["its_slab"] == par["its_1gpu"])
+        line["parity"] = par
+        line["config"]["parity"] = par
+        line["config"]["strong_scaling_base"] = {k: line["strong_scaling_base"][k] for k in
+                                                 ("n_gpus", "value", "speedup", "efficiency", "same_iterations_as_slab_run")}
     barrier()
     if rank == 0:
         print(json.dumps(line), flush=True)
+        if "parity" in line and not line["parity"]["ok"]:
+            dist.destroy_process_group()
+            raise SystemExit("PARITY FAILURE of the slab-decomposed solve: " + json.dumps(line["parity"]))
     dist.destroy_process_group()
 
 

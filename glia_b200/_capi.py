@@ -25,6 +25,10 @@ SIGNATURES = {
     "glia_rd_create_slab": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D, _I, _I]),
     "glia_rd_ipc_export": (_I, [_P, _I, _P]),
     "glia_rd_ipc_connect": (_I, [_P, _I, _P]),
+    "glia_rd_ipc_disconnect": (_I, [_P, _I]),
+    "glia_rd_wait_stream": (_I, [_P, _P]),
+    "glia_rd_set_splitting_order": (_I, [_P, _I]),
+    "glia_rd_set_two_snapshot": (_I, [_P, _P, _P]),
     "glia_rd_destroy": (_I, [_P]),
     "glia_rd_last_error": (C.c_char_p, [_P]),
     "glia_rd_stream": (_P, [_P]),

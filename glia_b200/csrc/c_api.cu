@@ -21,6 +21,7 @@ int guarded(glia_rd_t* h, F f) {
   if (!h) return 2;
   if (!h->eng) { h->err = "handle has no engine (creation failed)"; return 2; }
   try {
+    h->eng->v_make_current();
     f(*h->eng);
     return 0;
   } catch (const EngineError& e) {
@@ -35,7 +36,7 @@ int guarded(glia_rd_t* h, F f) {
 
 extern "C" {
 
-int glia_rd_abi_version(void) { return 1; }
+int glia_rd_abi_version(void) { return 2; }
 const char* glia_rd_build_info(void) {
 #if defined(GLIA_SIMT_EMU)
   return "simt-emulator (test only)";
@@ -87,8 +88,26 @@ int glia_rd_ipc_connect(glia_rd_t* h, int which, const void* handles) {
     E.v_ipc_connect(which, (const unsigned char*)handles);
   });
 }
+int glia_rd_ipc_disconnect(glia_rd_t* h, int which) {
+  return guarded(h, [&](EngineBase& E) { E.v_ipc_disconnect(which); });
+}
+int glia_rd_wait_stream(glia_rd_t* h, void* producer_stream) {
+  return guarded(h, [&](EngineBase& E) { E.v_wait_stream(producer_stream); });
+}
+int glia_rd_set_splitting_order(glia_rd_t* h, int order) {
+  return guarded(h, [&](EngineBase& E) {
+    if (order != 1 && order != 2) throw EngineError{"splitting order must be 1 or 2"};
+    E.v_set_order(order);
+  });
+}
+int glia_rd_set_two_snapshot(glia_rd_t* h, const void* d0, const void* obs0) {
+  return guarded(h, [&](EngineBase& E) { E.v_set_two_snapshot(d0, obs0); });
+}
 int glia_rd_destroy(glia_rd_t* h) {
   if (!h) return 0;
+  if (h->eng) {
+    try { h->eng->v_make_current(); } catch (...) {}
+  }
   delete h->eng;
   delete h;
   return 0;
@@ -177,7 +196,7 @@ int glia_rd_set_secondary_tissue(glia_rd_t* h, const void* wm, const void* gm, c
   return guarded(h, [&](EngineBase& E) { E.v_set_secondary_tissue(wm, gm, csf, k1, k2, k3); });
 }
 int glia_rd_objective_gradient(glia_rd_t* h, const void* c0, const void* d1, const void* obs, double beta,
-                               const void* wm, const void* gm, const void* csf, double J[3], void* g_c0, double g[6],
+                               const void* wm, const void* gm, const void* csf, double J[4], void* g_c0, double g[6],
                                int ksp_its[2]) {
   return guarded(h, [&](EngineBase& E) {
     if (!c0 || !d1 || !J || !g) throw EngineError{"objective_gradient: null argument"};

@@ -24,6 +24,8 @@ struct Comm {
   unsigned* flags[MAX_RANKS] = {};  // flags[q][s]: last epoch rank s announced to rank q
   double* red[MAX_RANKS] = {};      // red[q][(parity*MAX_RANKS + s)*RED_NV + i]
   int* err = nullptr;               // local: set when a wait timed out
+  int* done = nullptr;              // local: the PCG's `done` flag, raised on a time-out so that later kernels do no work
+  unsigned long long timeout_ns = 120ull * 1000000000ull;  // wall clock (GLIA_RD_PEER_TIMEOUT_S)
 };
 
 #if defined(GLIA_SIMT_EMU)
@@ -37,6 +39,10 @@ __device__ inline double ld_sys(const double* p) {
 }
 __device__ inline void fence_sys() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 __device__ inline void spin_pause() { std::this_thread::yield(); }
+__device__ inline unsigned long long now_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 #else
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -56,19 +62,35 @@ __device__ __forceinline__ double ld_sys(const double* p) {
 }
 __device__ __forceinline__ void fence_sys() { __threadfence_system(); }
 __device__ __forceinline__ void spin_pause() { __nanosleep(64); }
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 #endif
 
 // thread t < G: announce `epoch` to rank t, then wait until rank t has announced it to us.
-// A rank that never shows up (crashed peer) ends the wait after a bounded number of polls and
-// raises the local error flag instead of hanging the GPU.
+// A rank that never shows up (crashed peer) ends the wait after `timeout_ns` of WALL CLOCK (host skew
+// between ranks -- per-rank file reads, first-call module loads -- is legitimate and can be seconds), raises
+// the local error flag, which Engine::sync() turns into an error return of the call that was running, and
+// raises the PCG's done flag so that the kernels already enqueued behind it do not compute on partial data.
 __device__ inline void peer_signal_wait(const Comm& c, unsigned epoch, int t) {
   fence_sys();
   st_release_sys(c.flags[t] + c.rank, epoch);
   const unsigned* mine = c.flags[c.rank] + t;
-  long polls = 0;
+  unsigned long long t0 = 0;
+  unsigned polls = 0;
   while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
     spin_pause();
-    if (++polls > (1L << 27)) { *c.err = 1; break; }
+    if ((++polls & 1023u) == 0) {  // look at the clock every ~1000 polls
+      const unsigned long long now = now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > c.timeout_ns) {
+        *c.err = 1;
+        if (c.done) *c.done = 1;
+        break;
+      }
+    }
   }
 }
 

@@ -17,7 +17,6 @@
 #include "sweeps_dist.cuh"
 #include "sweeps_pipe.cuh"
 #include "sweeps_zpipe.cuh"
-#include "sweeps_v2.cuh"
 
 namespace glia {
 
@@ -58,11 +57,6 @@ inline int sm_count(int device) {
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
   return v;
 }
-inline size_t max_policy_window(int device) {
-  int v = 0;
-  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) != cudaSuccess || v < 0) { cudaGetLastError(); v = 0; }
-  return (size_t)v;
-}
 // the handle's stream gets the highest priority so that, when a side stream (below) has work in flight,
 // CTAs of the main stream's kernels are placed first on SMs as they free up
 inline int stream_create(cudaStream_t* s) {
@@ -92,6 +86,16 @@ struct Fork {
   void end(cudaStream_t main) { cudaEventRecord(join, side); cudaStreamWaitEvent(main, join, 0); }
 };
 inline void stream_destroy(cudaStream_t s) { cudaStreamDestroy(s); }
+// `consumer` waits for everything enqueued so far on `producer` (an event, no host synchronisation)
+inline int stream_wait_stream(cudaStream_t consumer, cudaStream_t producer) {
+  cudaEvent_t e;
+  int rc = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  if (rc) return rc;
+  rc = (int)cudaEventRecord(e, producer);
+  if (!rc) rc = (int)cudaStreamWaitEvent(consumer, e, 0);
+  cudaEventDestroy(e);  // released once the recorded work has completed
+  return rc;
+}
 inline const char* err_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 // per-launch CUDA-event profiler (off by default: zero overhead besides one branch)
 struct Profiler {
@@ -182,6 +186,7 @@ class Engine : public EngineBase {
   // slab decomposition along x (G = 1: the whole grid): this rank owns x-planes
   // [rank*n0l, (rank+1)*n0l) and sweeps the x lines with y in [rank*n1l, (rank+1)*n1l)
   int G = 1, rank = 0, n0l, n1l;
+  int device = 0;     // CUDA ordinal this handle lives on; every entry point makes it current (make_current)
   long nreal, ncplx;  // LOCAL element counts
   int n2c;            // n2/2: complex columns of the pair view
   cudaStream_t st = 0;
@@ -202,12 +207,6 @@ class Engine : public EngineBase {
   Comm comm;
   unsigned epoch = 0, rseq = 0;
   int nsm = 148;         // SMs of this device: grid size of the persistent (pipelined) sweeps
-  bool use_v2 = false;   // GLIA_RD_V2=1 selects the two-sequence packed FP32x2 D-sweeps (sweeps_v2.cuh); measured SLOWER at 256^3
-                         // (98-105 us vs 65-70 us: twice the shared-memory exchange traffic at E = 8)
-  bool use_pipe = true;  // GLIA_RD_PIPE=0 selects the one-tile-per-CTA kernels (A/B measurements)
-  int z_minb = 1;        // resident CTAs per SM the z second-derivative sweep is compiled for (GLIA_RD_ZMINB: 1, 3, 4).
-                         // Measured at 256^3 f32: 1 (123 registers, no cap) 49.6 us; 3 / 4 (80 / 64 registers) 82 us
-  int z_minb512 = 1;     // the same for 512-point z lines (168 registers uncapped = 1 CTA/SM; 2 caps at 128)
   // slab D-apply: run the rank-local z sweep on a side stream (into acc2) WHILE the peer x sweep, which is
   // NVLink-bound and leaves SM time unused, runs on a share of the SMs; the y sweep then takes acc + acc2
   // (the same two addends the serial order sums, so the result is bit-identical).  GLIA_RD_XZ=0/1.
@@ -237,13 +236,16 @@ class Engine : public EngineBase {
   C* tw[3] = {nullptr, nullptr, nullptr};
   double *partial = nullptr, *scal = nullptr;
   int* iscal = nullptr;
-  int* h_iscal = nullptr;     // pinned
+  int* h_iscal = nullptr;     // pinned (I_NISCAL ints, then one more: the comm error flag read by sync())
   double* h_out = nullptr;    // pinned
   long npart = 0;             // doubles per partial region
   int its_guess = 2;
   // time stepping
   int nt = 0;
   T dt = 0;
+  int order = 2;               // params->tu_->order_: 2 = Strang, 1 = diffusion(dt) then reaction
+  T *d0 = nullptr, *obs0 = nullptr;  // two_time_points_: data and observation mask at t = 0 (owned copies)
+  bool two_snap = false, has_obs0 = false;
   T *c_hist = nullptr, *p_hist = nullptr, *chalf_hist = nullptr;
   T *c_t = nullptr, *p_0 = nullptr, *work11 = nullptr, *Tk = nullptr, *Tr = nullptr;
   T *stage = nullptr, *TkX = nullptr;  // G > 1 only
@@ -263,7 +265,7 @@ class Engine : public EngineBase {
 
   int precision() const override { return (int)sizeof(T); }
 
-  Engine(const int nn[3], int device, double dt_ctx_, int rank_ = 0, int nranks_ = 1) {
+  Engine(const int nn[3], int device_, double dt_ctx_, int rank_ = 0, int nranks_ = 1) {
     for (int i = 0; i < 3; ++i) {
       n[i] = nn[i];
       if (!(n[i] == 32 || n[i] == 64 || n[i] == 128 || n[i] == 256 || n[i] == 512))
@@ -276,24 +278,16 @@ class Engine : public EngineBase {
     n0l = n[0] / G;
     n1l = n[1] / G;
     if (n0l < 1 || n1l < 1 || (long)n0l * n[1] < 2) throw EngineError{"grid too small for this many slabs"};
+    device = device_;
     GLIA_CHECK(rt::set_device(device));
     GLIA_CHECK(rt::stream_create(&st));
     nsm = rt::sm_count(device);
-    if (const char* e = std::getenv("GLIA_RD_PIPE")) use_pipe = std::atoi(e) != 0;
-    if (const char* e = std::getenv("GLIA_RD_V2")) use_v2 = std::atoi(e) != 0;
-    if (const char* e = std::getenv("GLIA_RD_L2WIN")) use_window = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_PDL")) use_pdl = std::atoi(e) != 0;
-    if (const char* e = std::getenv("GLIA_RD_ZPIPE")) use_zpipe = std::atoi(e) != 0;
-    if (const char* e = std::getenv("GLIA_RD_C2C_PIPE")) use_c2c_pipe = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_PDL_SLAB")) use_pdl_slab = std::atoi(e) != 0;
-    if (use_v2) use_pdl = false;  // the packed sweeps (sweeps_v2.cuh) carry no pdl_wait()
-    max_window = rt::max_policy_window(device);
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
-    if (const char* e = std::getenv("GLIA_RD_ZMINB")) z_minb = std::atoi(e);
-    if (const char* e = std::getenv("GLIA_RD_ZMINB512")) z_minb512 = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_XZ")) use_xz = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_XZ_CTAS")) xz_ctas = std::atoi(e);
-    if (G == 1 || !use_pipe || use_v2 || (sizeof(T) == 8 && (n[0] > 256 || n[1] > 256))) use_xz = false;
+    if (G == 1 || (sizeof(T) == 8 && (n[0] > 256 || n[1] > 256))) use_xz = false;
     if (use_xz) GLIA_CHECK(fork.create());
     timer.create();
     nreal = (long)n0l * n[1] * n[2];
@@ -335,12 +329,19 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL, st));
     GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL, st));
     comm.err = iscal + I_COMM_ERR;
-    GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * I_NISCAL));
+    comm.done = iscal + I_DONE;
+    if (const char* e = std::getenv("GLIA_RD_PEER_TIMEOUT_S")) {
+      const double sec = std::atof(e);
+      if (sec > 0) comm.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
+    GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * (I_NISCAL + 1)));
+    h_iscal[I_NISCAL] = 0;
     GLIA_CHECK(rt::host_malloc((void**)&h_out, sizeof(double) * 16));
     sym = PcSym<T>{dt_ctx, (T)0, (T)0, (T)0, (T)(1.0 / ((double)n[0] * n[1] * n[2]))};
     GLIA_CHECK(rt::sync(st));
   }
   ~Engine() override {
+    rt::set_device(device);
     rt::sync(st);
     for (int q = 0; q < G; ++q) {
       if (q == rank) continue;
@@ -355,6 +356,7 @@ class Engine : public EngineBase {
     rt::host_free(hs_in); rt::host_free(hs_out);
     for (int a = 0; a < 3; ++a) rt::dev_free(symtab[a]);
     rt::dev_free(phi_filter); rt::dev_free(phi_dots);
+    rt::dev_free(d0); rt::dev_free(obs0);
     timer.destroy();
     prof.destroy();
     fork.destroy();
@@ -391,6 +393,20 @@ class Engine : public EngineBase {
     }
     if (which == 0) { bind_comm(comm_off); connected = true; }
     else hist_connected = true;
+  }
+  // Close this rank's mappings of the peers' arenas (which: 0 work arena, 1 histories, -1 both).  CUDA leaves
+  // freeing an exported allocation that another process still has open undefined, so teardown (and every
+  // re-allocation of the histories) is: every rank disconnects -> caller-side barrier -> free.
+  void ipc_disconnect(int which) {
+    if (G <= 1) return;
+    sync();
+    for (int q = 0; q < G; ++q) {
+      if (q == rank) continue;
+      if ((which == 0 || which < 0) && peer_arena[q]) { rt::ipc_close(peer_arena[q], arena_bytes); peer_arena[q] = nullptr; }
+      if ((which == 1 || which < 0) && peer_hist[q]) { rt::ipc_close(peer_hist[q], hist_bytes); peer_hist[q] = nullptr; }
+    }
+    if (which == 0 || which < 0) connected = false;
+    if (which == 1 || which < 0) hist_connected = false;
   }
   bool in_arena(const void* ptr) const {
     return (const char*)ptr >= arena && (const char*)ptr < arena + arena_bytes;
@@ -448,8 +464,6 @@ class Engine : public EngineBase {
   // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
   // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
   // Off while profiling: the bracketing events would serialise the launches anyway.
-  bool use_zpipe = false;  // GLIA_RD_ZPIPE=1: persistent warp-private pipelined z second-derivative sweep (unmeasured)
-  bool use_c2c_pipe = true;  // GLIA_RD_C2C_PIPE=0: one-tile-per-CTA form of the preconditioner's y sweeps
   bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
   // slab handles: only the rank-local chains (z, y sweeps, scalar kernels, vector update) overlap; the
   // peer x sweeps and the k_peer_barrier launches around them go through L() and stay fully serialised,
@@ -465,25 +479,25 @@ class Engine : public EngineBase {
     ++launches;
 #endif
   }
-  // the same with `win` (one field) marked streaming for L2 in this launch; no-op for fields beyond the
-  // device's window limit (512^3: nothing fits in L2 anyway) or when GLIA_RD_L2WIN=0
-  size_t max_window = 0;
-  bool use_window = false;  // GLIA_RD_L2WIN=1 (measured: no gain at 256^3, see fft_core.cuh)
-  template <class... KA, class... A>
-  void LS(const void* win, const char* tag, void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... args) {
-    const size_t bytes = sizeof(T) * (size_t)nreal;
-    const bool ok = use_window && GLIA_L2_HINTS && win && bytes <= max_window;
-    if (!ok) return LP(tag, k, g, b, smem, s, args...);
-    const int slot = prof.before(tag, s);
-    simt::launch_streaming(ok ? win : nullptr, bytes, k, g, b, smem, s, args...);
-    prof.after(slot, s);
-    ++launches;
-  }
   void check_launch() {
     const char* e = simt::last_error();
     if (e) throw EngineError{std::string("kernel launch: ") + e};
   }
-  void sync() { GLIA_CHECK(rt::sync(st)); check_launch(); }
+  // End of every entry point.  Slab handles also look at the peer-wait error flag here, so that a collective
+  // that synchronises without solving (set_diffusion, gradient, ...) cannot return success after a rank
+  // barrier timed out; the flag is cleared so that the handle stays usable once the peers are back.
+  void sync() {
+    if (G > 1) GLIA_CHECK(rt::d2h(h_iscal + I_NISCAL, iscal + I_COMM_ERR, sizeof(int), st));
+    GLIA_CHECK(rt::sync(st));
+    check_launch();
+    if (G > 1 && h_iscal[I_NISCAL]) {
+      h_iscal[I_NISCAL] = 0;
+      rt::zero(iscal + I_COMM_ERR, sizeof(int), st);
+      rt::sync(st);
+      throw EngineError{"slab peer did not arrive at a rank barrier (timed out after GLIA_RD_PEER_TIMEOUT_S)"};
+    }
+  }
+  void make_current() { GLIA_CHECK(rt::set_device(device)); }
 
   // ------------------------------------------------------------ geometry ----
   TileS tile_y() const { return TileS{(long)n2c, (long)n[1] * n2c, n2c / SL, n0l, 0}; }
@@ -512,35 +526,19 @@ class Engine : public EngineBase {
   void sweep_deriv2_z(const char* tag, const T* x, const T* kfield, const int* done) {
     T* const zo = z_out_override ? z_out_override : acc;
     const cudaStream_t zs = z_side ? fork.side : st;
-    if (use_zpipe) {  // round-2 candidate, see sweeps_zpipe.cuh
-      bool launched = false;
-      GLIA_DISPATCH_N(n[2], {
-        if (zpipe_fits<T, N>()) {
-          const long np = lines_z().npairs;
-          const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());
-          const int cap = nsm * zpipe_ctas<T, N>();
-          LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(ngroups < cap ? ngroups : cap)), dim3(zthreads<N>()),
-             zpipe_smem<T, N>(), zs, lines_z(), ngroups, x, kfield, zo, (const C*)tw[2], done);
-          launched = true;
-        }
-      });
-      if (launched) return;
-    }
     GLIA_DISPATCH_N(n[2], {
-      // register budget: 3-4 resident CTAs only pay for the 256-thread single-precision shapes
-      const bool small = sizeof(T) == 4 && N <= 256;
-      if (small && z_minb == 4)
-        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 4 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs,
-          lines_z(), x, kfield, zo, (const C*)tw[2], done);
-      else if (small && z_minb == 3)
-        LP(tag, kz_deriv2<T, N, ADD, (sizeof(T) == 4 && N <= 256) ? 3 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs,
-          lines_z(), x, kfield, zo, (const C*)tw[2], done);
-      else if (sizeof(T) == 4 && (z_minb == 2 || (z_minb512 == 2 && N == 512)))
-        LP(tag, kz_deriv2<T, N, ADD, sizeof(T) == 4 ? 2 : 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs, lines_z(), x,
-          kfield, zo, (const C*)tw[2], done);
-      else
+      if constexpr (zpipe_fits<T, N>()) {
+        // persistent warp-private pipelined form (sweeps_zpipe.cuh; measured: 49.7 -> 45.8 us at 256^3,
+        // 603 -> 526 us at 512^3, profiles/r2d_zpipe_twldg_ab.txt)
+        const long np = lines_z().npairs;
+        const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());
+        const int cap = nsm * zpipe_ctas<T, N>();
+        LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(ngroups < cap ? ngroups : cap)), dim3(zthreads<N>()),
+           zpipe_smem<T, N>(), zs, lines_z(), ngroups, x, kfield, zo, (const C*)tw[2], done);
+      } else {
         LP(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs, lines_z(), x, kfield, zo,
-          (const C*)tw[2], done);
+           (const C*)tw[2], done);
+      }
     });
   }
   static RowsS<T> rows_s(const TileS& g, const void* ptr) {
@@ -556,37 +554,29 @@ class Engine : public EngineBase {
                          T* out2, double* pp, const int* done, const T* acc_extra = nullptr) {
     constexpr bool keep_x = (EPI == EPI_MATVEC || EPI == EPI_RHS);
     int nblk = 0;
-    if constexpr (std::is_same<T, float>::value) {
-      if (use_v2 && SL == 16) {  // packed FP32x2 line FFTs (sweeps_v2.cuh)
-        GLIA_DISPATCH_N(nline, {
-          const int ntiles = g.nchunk * g.n_outer;
-          const int cap = nsm * v2_ctas<N>();
-          nblk = ntiles < cap ? ntiles : cap;
-          LS(x, tag, ks2_deriv2_pipe<N, EPI, RowsS<float>, RowsS<float>, RowsS<float>, RowsS<float>>, dim3((unsigned)nblk),
-             dim3(N), v2_smem<N>(), st, ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1),
-             rows_s(g, out2), (const cplx<float>*)tw_for(nline, g), (float)alpha, pp, done);
-        });
-        return nblk;
-      }
-    }
     GLIA_DISPATCH_N(nline, {
-      if (use_pipe && pipe_fits<T, N>()) {
+      if constexpr (pipe_fits<T, N>()) {
         const int ntiles = g.nchunk * g.n_outer;
         const dim3 gr = grid_pipe<N>(ntiles);
         nblk = (int)gr.x;
+        bool launched = false;
         if constexpr (EPI != EPI_ADD && EPI != EPI_SET) {
           if (acc_extra) {
             const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk};
-            LS(x, tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
+            LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
                st, ntiles, rows_s(g, x), rows_s(g, kfield), a2, rows_s(g, out1), rows_s(g, out2),
                (const C*)tw_for(nline, g), alpha, pp, done);
-            return nblk;
+            launched = true;
           }
         }
-        LS(x, tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
-          ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2), (const C*)tw_for(nline, g),
-          alpha, pp, done);
-      } else {
+        if (!launched)
+          LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
+             ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2),
+             (const C*)tw_for(nline, g), alpha, pp, done);
+      } else {  // three tiles exceed shared memory (double precision at 512 points): one tile per CTA
+        if (acc_extra) throw EngineError{"internal: two-field accumulator needs the pipelined sweep"};
+        if (keep_x && smem_s2<N>() > 227 * 1024)
+          throw EngineError{"512-point lines in double precision: the operatorA sweep does not fit shared memory"};
         nblk = (int)grid_s(g).x;
         L(tag, ks_deriv2<T, N, EPI>, grid_s(g), block_s<N>(), keep_x ? smem_s2<N>() : smem_s<N>(), st, g, (const C*)x,
           (const C*)kfield, (const C*)acc, (const C*)tw_for(nline, g), alpha, (C*)out1, (C*)out2, pp, done);
@@ -615,7 +605,7 @@ class Engine : public EngineBase {
     }
     barrier();
     GLIA_DISPATCH_N(n[0], {
-      if (use_pipe && pipe_fits<T, N>()) {
+      if constexpr (pipe_fits<T, N>()) {
         const int ntiles = txd.nchunk * txd.n_outer;
         const RowsX<T> rx{xr, txd}, ra{ar, txd};
         dim3 gx = grid_pipe<N>(ntiles);
@@ -661,7 +651,7 @@ class Engine : public EngineBase {
                                          (const C*)tw[2], done));
     }
     GLIA_DISPATCH_N(n[1], {
-      if (use_c2c_pipe && use_pipe && pipe_fits<T, N>()) {
+      if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
         LP("ks_c2c.y", ks_c2c_pipe<T, N, -1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
            rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
@@ -675,7 +665,7 @@ class Engine : public EngineBase {
       const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
       barrier();
       GLIA_DISPATCH_N(n[0], {
-        if (use_pipe && pipe_fits<T, N>()) {
+        if constexpr (pipe_fits<T, N>()) {
           const int ntiles = txd.nchunk * txd.n_outer;
           L("kx_pc_dist", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
             RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], done);
@@ -687,7 +677,7 @@ class Engine : public EngineBase {
       barrier();
     } else {
       GLIA_DISPATCH_N(n[0], {
-        if (use_pipe && pipe_fits<T, N>()) {
+        if constexpr (pipe_fits<T, N>()) {
           const int ntiles = tx.nchunk * tx.n_outer;
           LP("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
             rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
@@ -697,7 +687,7 @@ class Engine : public EngineBase {
       });
     }
     GLIA_DISPATCH_N(n[1], {
-      if (use_c2c_pipe && use_pipe && pipe_fits<T, N>()) {
+      if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
         LP("ks_c2c.y", ks_c2c_pipe<T, N, +1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
            rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
@@ -838,12 +828,11 @@ class Engine : public EngineBase {
 
   void fetch_iscal() {
     GLIA_CHECK(rt::d2h(h_iscal, iscal, sizeof(int) * I_NISCAL, st));
-    sync();
-    if (h_iscal[I_COMM_ERR]) throw EngineError{"slab peer did not arrive at a rank barrier (timed out)"};
+    sync();  // (throws if a peer wait timed out)
   }
 
   // one PCG iteration, enqueued without synchronisation; `it` is 1-based
-  void enqueue_iteration(T* x, T dt_solve, int it) {
+  void enqueue_iteration(T* x, const T* xin, T dt_solve, int it) {
     const int* done = iscal + I_DONE;
     const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
     const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
@@ -852,23 +841,30 @@ class Engine : public EngineBase {
     const int nb2 = pc_apply(r, w, z, true, part(1), done);
     LP("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
       comm, G > 1 ? next_epoch() : 0u, rseq++);
-    LP("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, x, p, (const T*)z, (const double*)scal,
-                 (const int*)iscal, it);
+    LP("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, (const T*)(it == 1 ? xin : x), x, p,
+       (const T*)z, (const double*)scal, (const int*)iscal, it);
   }
 
-  // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.
-  int diffusion_solve(T* x, double dt_in) {
-    if (G > 1 && !in_arena(x)) {  // the rhs x sweep reads x through the peer mappings
-      GLIA_CHECK(rt::copy(stage, x, sizeof(T) * nreal, st));
+  // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.  With `xin` the solve starts from that
+  // field and leaves the result in x (out of place: xin is only read); without, in place like the reference.
+  int diffusion_solve(T* x, double dt_in, const T* xin = nullptr) {
+    if (xin == x) xin = nullptr;
+    if (G > 1 && (!(in_arena(x) || in_hist(x)) || (xin && !(in_arena(xin) || in_hist(xin))))) {
+      // the rhs x sweep reads its operand through the peer mappings
+      GLIA_CHECK(rt::copy(stage, xin ? xin : x, sizeof(T) * nreal, st));
       const int its = diffusion_solve(stage, dt_in);
       GLIA_CHECK(rt::copy(x, stage, sizeof(T) * nreal, st));
       return its;
     }
     const T dts = (T)dt_in;
     dt_ctx = dts;  // side effect on later prec_factor() calls (trap T2)
-    if (k_scale == (T)0) return 0;
+    const T* src = xin ? xin : x;
+    if (k_scale == (T)0) {
+      if (xin) GLIA_CHECK(rt::copy(x, xin, sizeof(T) * nreal, st));
+      return 0;
+    }
     const T alph = (T)(1.0 / 2.0 * (double)dts);
-    dapply<EPI_RHS>(x, kf, alph, b, r, nullptr, nullptr);
+    dapply<EPI_RHS>(src, kf, alph, b, r, nullptr, nullptr);
     const int nb0 = pc_apply(b, nullptr, nullptr, false, part(2), nullptr);
     const int nb1 = pc_apply(r, nullptr, p, true, part(1), nullptr);
     L("k_pcg_init", k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
@@ -877,7 +873,7 @@ class Engine : public EngineBase {
     // speculate: enqueue as many iterations as the previous solve needed, then look
     int burst = its_guess < 1 ? 1 : its_guess;
     for (;;) {
-      for (int j = 0; j < burst; ++j) enqueue_iteration(x, dts, ++it);
+      for (int j = 0; j < burst; ++j) enqueue_iteration(x, src, dts, ++it);
       fetch_iscal();
       if (h_iscal[I_DONE]) break;
       burst = 1;
@@ -886,6 +882,7 @@ class Engine : public EngineBase {
     const int its = h_iscal[I_ITS];
     if (h_iscal[I_REASON] < 0 && h_iscal[I_REASON] != KSP_DIVERGED_ITS)
       throw EngineError{"KSP diverged, reason " + std::to_string(h_iscal[I_REASON])};
+    if (its == 0 && xin) GLIA_CHECK(rt::copy(x, xin, sizeof(T) * nreal, st));  // converged at the iteration-0 test
     its_guess = its;
     return its;
   }
@@ -918,11 +915,13 @@ class Engine : public EngineBase {
     if (which == 2 && i >= 0 && i < nt) return chalf_hist + (long)i * nreal;
     throw EngineError{"history index out of range"};
   }
-  void reaction(T* ct, const T* clin, T dtr, T* chalf_out) {
+  // ct <- R(cin) (cin == nullptr: in place), nonlinear or linearised about clin
+  void reaction(T* ct, const T* clin, T dtr, T* chalf_out, const T* cin = nullptr) {
+    const T* in = cin ? cin : ct;
     if (clin)
-      L("k_reaction_lin", k_reaction_lin<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, clin, dtr);
+      L("k_reaction_lin", k_reaction_lin<T>, grid_pw(nreal), dim3(256), 0, st, nreal, in, ct, (const T*)rho, clin, dtr);
     else
-      L("k_reaction", k_reaction<T>, grid_pw(nreal), dim3(256), 0, st, nreal, ct, (const T*)rho, dtr, chalf_out);
+      L("k_reaction", k_reaction<T>, grid_pw(nreal), dim3(256), 0, st, nreal, in, ct, (const T*)rho, dtr, chalf_out);
   }
   // PdeOperatorsRD::solveIncremental
   void solve_incremental(T* ctil, int i, int mode, T dth) {
@@ -933,18 +932,29 @@ class Engine : public EngineBase {
   }
   int solve_state(const T* c0, T* cT, int linearized) {
     if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
-    GLIA_CHECK(rt::copy(c_t, c0, sizeof(T) * nreal, st));
-    if (linearized == 0) GLIA_CHECK(rt::copy(hist(0, 0), c_t, sizeof(T) * nreal, st));
     int total = 0;
     const double dth = (double)dt / 2.0;
-    for (int i = 0; i < nt; ++i) {
-      if (linearized == 2) solve_incremental(c_t, i, 1, (T)dth);
-      total += diffusion_solve(c_t, dth);
-      if (linearized == 0) reaction(c_t, nullptr, dt, hist(2, i));
-      else reaction(c_t, hist(0, i), dt, nullptr);
-      total += diffusion_solve(c_t, dth);
-      if (linearized == 2) solve_incremental(c_t, i, 2, (T)dth);
-      if (linearized == 0) GLIA_CHECK(rt::copy(hist(0, i + 1), c_t, sizeof(T) * nreal, st));
+    if (linearized == 0) {
+      // The state walks through the history slots themselves: c_[i] --solve--> c_half_[i] --reaction--> c_[i+1]
+      // --solve in place--> c_[i+1].  The stores of PdeOperators.cpp:252, 277, 300 cost nothing.
+      GLIA_CHECK(rt::copy(hist(0, 0), c0, sizeof(T) * nreal, st));
+      for (int i = 0; i < nt; ++i) {
+        total += diffusion_solve(hist(2, i), order == 2 ? dth : (double)dt, hist(0, i));
+        reaction(hist(0, i + 1), nullptr, dt, nullptr, hist(2, i));
+        if (order == 2) total += diffusion_solve(hist(0, i + 1), dth);
+      }
+      GLIA_CHECK(rt::copy(c_t, hist(0, nt), sizeof(T) * nreal, st));
+    } else {
+      GLIA_CHECK(rt::copy(c_t, c0, sizeof(T) * nreal, st));
+      for (int i = 0; i < nt; ++i) {
+        if (linearized == 2) solve_incremental(c_t, i, 1, (T)dth);
+        total += diffusion_solve(c_t, order == 2 ? dth : (double)dt);
+        reaction(c_t, hist(0, i), dt, nullptr);
+        if (order == 2) {
+          total += diffusion_solve(c_t, dth);
+          if (linearized == 2) solve_incremental(c_t, i, 2, (T)dth);
+        }
+      }
     }
     if (cT && cT != c_t) GLIA_CHECK(rt::copy(cT, c_t, sizeof(T) * nreal, st));
     sync();
@@ -957,18 +967,19 @@ class Engine : public EngineBase {
     int total = 0;
     const double dth = (double)dt / 2.0;
     for (int i = 0; i < nt; ++i) {
-      total += diffusion_solve(p_0, dth);
       const int it = nt - i - 1;
+      // the adjoint walks through p_[.]: p_[it+1] --solve--> p_0 (work) --reaction--> p_[it] --solve in place--> p_[it]
+      // (p_[nt] itself is only a valid source when this call wrote it: trap T4)
+      total += diffusion_solve(p_0, order == 2 ? dth : (double)dt, i == 0 ? nullptr : (const T*)hist(1, it + 1));
       const T* clin = hist(2, it);
-      if (!adjoint_store) {
-        GLIA_CHECK(rt::copy(work11, hist(0, it), sizeof(T) * nreal, st));
-        total += diffusion_solve(work11, dth);
+      if (!adjoint_store) {  // reactionAdjoint re-diffuses c_[it] by dt/2 (PdeOperators.cpp:330-340), whatever the order
+        total += diffusion_solve(work11, dth, hist(0, it));
         clin = work11;
       }
-      reaction(p_0, clin, dt, nullptr);
-      total += diffusion_solve(p_0, dth);
-      GLIA_CHECK(rt::copy(hist(1, it), p_0, sizeof(T) * nreal, st));
+      reaction(hist(1, it), clin, dt, nullptr, p_0);
+      if (order == 2) total += diffusion_solve(hist(1, it), dth);
     }
+    GLIA_CHECK(rt::copy(p_0, hist(1, 0), sizeof(T) * nreal, st));
     if (p0out && p0out != p_0) GLIA_CHECK(rt::copy(p0out, p_0, sizeof(T) * nreal, st));
     sync();
     return total;
@@ -1024,9 +1035,9 @@ class Engine : public EngineBase {
     sync();
   }
   // t = O c - d1, pT = -O^T t into Tr; returns { <t,t>, <c0,c0> } summed over all ranks
-  void terminal_condition(const T* c, const T* d1, const T* obs, const T* c0, double sums[2]) {
+  void terminal_condition(const T* c, const T* d1, const T* obs, const T* c0, double sums[2], T* pT_out) {
     const dim3 g = grid_pw(nreal);
-    L("k_obs_mismatch", k_obs_mismatch<T>, g, dim3(256), 0, st, nreal, c, d1, obs, c0, Tr, part(0));
+    L("k_obs_mismatch", k_obs_mismatch<T>, g, dim3(256), 0, st, nreal, c, d1, obs, c0, pT_out, part(0));
     L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8, comm,
       G > 1 ? next_epoch() : 0u, rseq++);
     GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
@@ -1036,22 +1047,31 @@ class Engine : public EngineBase {
   }
   double lebesgue() const { return (2.0 * M_PI / n[0]) * (2.0 * M_PI / n[1]) * (2.0 * M_PI / n[2]); }
   // DerivativeOperatorsRD::evaluateObjectiveAndGradient in field space
-  // (src/grad/DerivativeOperatorsRD.cpp:130-226): J[3] = {J, mismatch term, regularisation},
+  // (src/grad/DerivativeOperatorsRD.cpp:130-226): J[4] = {J, mismatch term, regularisation, t = 0 mismatch},
   // g_c0 = -h^3 (alpha(0) - beta c0)  (g_p = Phi^T g_c0), g[6] as grad_kappa_rho.
   void objective_gradient(const T* c0, const T* d1, const T* obs, double beta, const T* wm, const T* gm, const T* csf,
-                          double J[3], T* g_c0, double g[6], int ksp[2]) {
+                          double J[4], T* g_c0, double g[6], int ksp[2]) {
     const double leb = lebesgue();
+    double sums[2], m0 = 0.0;
+    if (two_snap) {  // ||O0 c(0) - d0||^2 ; Tk <- -O0^T(O0 c0 - d0), kept for the gradient term below (:149-153)
+      terminal_condition(c0, d0, has_obs0 ? obs0 : nullptr, nullptr, sums, Tk);
+      m0 = sums[0];
+    }
     ksp[0] = solve_state(c0, nullptr, 0);
-    double sums[2];
-    terminal_condition(c_t, d1, obs, c0, sums);
+    terminal_condition(c_t, d1, obs, c0, sums, Tr);
     J[1] = leb * 0.5 * sums[0];
     J[2] = 0.5 * beta * sums[1] * leb;
-    J[0] = J[1] + J[2];
+    J[3] = leb * 0.5 * m0;
+    J[0] = leb * 0.5 * (sums[0] + m0) + J[2];
     ksp[1] = solve_adjoint(Tr, nullptr, 1, 1);
     if (g_c0) {  // p0 - beta c0, then scaled by -h^3 (VecAXPY, VecScale)
       L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, g_c0, (T)1, (const T*)p_0, (T)(-beta), c0);
       L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, g_c0, (T)(-leb), (const T*)g_c0, (T)0,
         (const T*)nullptr);
+      // + h^3 O0^T(O0 c0 - d0)  (DerivativeOperatorsRD.cpp:216-222; Tk holds its negative)
+      if (two_snap)
+        L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, g_c0, (T)1, (const T*)g_c0, (T)(-leb),
+          (const T*)Tk);
     }
     grad_kappa_rho(wm, gm, csf, g);
   }
@@ -1059,12 +1079,13 @@ class Engine : public EngineBase {
   // y_c0 = h^3 (beta c0~ - alpha~(0)) [- h^3 alpha~_k(0)]; hk = h^3 <wm|gm|csf, T_kp>, <wm|gm|csf, T_kk>.
   void hessian_matvec(const T* c0t, const T* obs, double beta, int diffusivity_inversion, const T* wm, const T* gm,
                       const T* csf, T* y_c0, double hk[6], int ksp[4]) {
+    if (two_snap) throw EngineError{"Hessian currently not implemented for two-snapshot scenario"};  // DerivativeOperatorsRD.cpp:234
     const double leb = lebesgue();
     double sums[2], gtmp[6];
     for (int i = 0; i < 6; ++i) hk[i] = 0;
     for (int i = 0; i < 4; ++i) ksp[i] = 0;
     ksp[0] = solve_state(c0t, nullptr, 1);
-    terminal_condition(c_t, nullptr, obs, nullptr, sums);
+    terminal_condition(c_t, nullptr, obs, nullptr, sums, Tr);
     ksp[1] = solve_adjoint(Tr, nullptr, 2, 1);
     // y = beta c0~ - p0 ; y *= h^3
     L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, y_c0, (T)beta, c0t, (T)-1, (const T*)p_0);
@@ -1074,7 +1095,7 @@ class Engine : public EngineBase {
     for (int i = 0; i < 3; ++i) hk[i] = gtmp[i];
     GLIA_CHECK(rt::zero(Tr, sizeof(T) * nreal, st));
     ksp[2] = solve_state(Tr, nullptr, 2);
-    terminal_condition(c_t, nullptr, obs, nullptr, sums);
+    terminal_condition(c_t, nullptr, obs, nullptr, sums, Tr);
     ksp[3] = solve_adjoint(Tr, nullptr, 2, 1);
     L("k_axpby", k_axpby<T>, grid_pw(nreal), dim3(256), 0, st, nreal, y_c0, (T)(-leb), (const T*)p_0, (T)1, (const T*)y_c0);
     grad_kappa_rho(wm, gm, csf, gtmp);
@@ -1099,16 +1120,20 @@ class Engine : public EngineBase {
     for (int i = 0; i < reps; ++i) {
       if (what == 0) {
         const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
-        GLIA_DISPATCH_N(n[0], L("probe", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st,
-                                           ntiles, RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1],
-                                           (const int*)nullptr));
+        GLIA_DISPATCH_N(n[0], {
+          if constexpr (pipe_fits<T, N>())
+            L("probe", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
+              RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], (const int*)nullptr);
+        });
       } else {
         const PeerRows<T> xr = rows(p, 1), ar = rows(acc, 2);
         const RowsX<T> rx{xr, txd}, ra{ar, txd};
-        GLIA_DISPATCH_N(n[0], L("probe", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>,
-                                           grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx,
-                                           RowsPen<T>{(C*)kT, txd}, ra, ra, ra, (const C*)tw[0], (T)0, (double*)nullptr,
-                                           (const int*)nullptr));
+        GLIA_DISPATCH_N(n[0], {
+          if constexpr (pipe_fits<T, N>())
+            L("probe", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, grid_pipe<N>(ntiles),
+              block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)kT, txd}, ra, ra, ra, (const C*)tw[0], (T)0,
+              (double*)nullptr, (const int*)nullptr);
+        });
       }
     }
     const double ms = timer.stop_ms(st);
@@ -1353,6 +1378,7 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------- type-erased face ----
   void* stream_handle() override { return (void*)(intptr_t)st; }
+  void v_make_current() override { make_current(); }
   void v_fft_r2c(const void* f, void* fhat) override {
     if (G > 1) throw EngineError{"glia_rd_fft_r2c: the stand-alone 3-D FFT is single-GPU; slab handles transform inside the sweeps"};
     fft3d_r2c(*this, (const T*)f, (C*)fhat);
@@ -1363,6 +1389,21 @@ class Engine : public EngineBase {
   }
   void v_ipc_export(int which, unsigned char* out) override { ipc_export(which, out); }
   void v_ipc_connect(int which, const unsigned char* handles) override { ipc_connect(which, handles); }
+  void v_ipc_disconnect(int which) override { ipc_disconnect(which); }
+  void v_wait_stream(void* producer) override { GLIA_CHECK(rt::stream_wait_stream(st, (cudaStream_t)(intptr_t)producer)); }
+  void v_set_order(int o) override { order = o; }
+  void v_set_two_snapshot(const void* d0_, const void* obs0_) override {
+    two_snap = d0_ != nullptr;
+    has_obs0 = two_snap && obs0_ != nullptr;
+    if (!two_snap) return;
+    if (!d0) GLIA_CHECK(rt::dev_malloc((void**)&d0, sizeof(T) * nreal));
+    GLIA_CHECK(rt::copy(d0, d0_, sizeof(T) * nreal, st));
+    if (has_obs0) {
+      if (!obs0) GLIA_CHECK(rt::dev_malloc((void**)&obs0, sizeof(T) * nreal));
+      GLIA_CHECK(rt::copy(obs0, obs0_, sizeof(T) * nreal, st));
+    }
+    sync();
+  }
   void v_gradient(void* gx, void* gy, void* gz, const void* x, int m) override {
     gradient((T*)gx, (T*)gy, (T*)gz, (const T*)x, m);
   }
@@ -1418,7 +1459,7 @@ class Engine : public EngineBase {
     set_secondary_tissue((const T*)wm, (const T*)gm, (const T*)csf, k1, k2, k3);
   }
   void v_objective_gradient(const void* c0, const void* d1, const void* obs, double beta, const void* wm, const void* gm,
-                            const void* csf, double J[3], void* g_c0, double g[6], int ksp[2]) override {
+                            const void* csf, double J[4], void* g_c0, double g[6], int ksp[2]) override {
     objective_gradient((const T*)c0, (const T*)d1, (const T*)obs, beta, (const T*)wm, (const T*)gm, (const T*)csf, J,
                        (T*)g_c0, g, ksp);
   }

@@ -17,8 +17,14 @@ class EngineBase {
   long long launches = 0;
   virtual int precision() const = 0;
   virtual void* stream_handle() = 0;
+  // the CUDA device is per-host-thread state: every C-ABI entry makes the handle's device current first
+  virtual void v_make_current() = 0;
   virtual void v_ipc_export(int which, unsigned char* out64) = 0;
   virtual void v_ipc_connect(int which, const unsigned char* handles) = 0;
+  virtual void v_ipc_disconnect(int which) = 0;
+  virtual void v_wait_stream(void* producer_stream) = 0;
+  virtual void v_set_order(int order) = 0;
+  virtual void v_set_two_snapshot(const void* d0, const void* obs0) = 0;
   virtual void v_fft_r2c(const void* f, void* fhat) = 0;
   virtual void v_fft_c2r(const void* fhat, void* f) = 0;
   virtual void v_gradient(void* gx, void* gy, void* gz, const void* x, int mask) = 0;
@@ -44,7 +50,7 @@ class EngineBase {
   virtual void v_grad_kappa_rho(const void* wm, const void* gm, const void* csf, double out[6]) = 0;
   virtual void v_set_secondary_tissue(const void* wm, const void* gm, const void* csf, double k1, double k2, double k3) = 0;
   virtual void v_objective_gradient(const void* c0, const void* d1, const void* obs, double beta, const void* wm,
-                                    const void* gm, const void* csf, double J[3], void* g_c0, double g[6], int ksp[2]) = 0;
+                                    const void* gm, const void* csf, double J[4], void* g_c0, double g[6], int ksp[2]) = 0;
   virtual void v_hessian_matvec(const void* c0t, const void* obs, double beta, int diffusivity_inversion, const void* wm,
                                 const void* gm, const void* csf, void* y_c0, double hk[6], int ksp[4]) = 0;
   virtual void v_smooth(void* out, const void* in, double sigma) = 0;

@@ -32,100 +32,28 @@ __device__ __forceinline__ cplx<T> cmulc(cplx<T> a, cplx<T> b) {  // a * conj(b)
   return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
 }
 
-// ---------------------------------------------- packed FP32x2 arithmetic ----
-// Blackwell (sm_100) issues two FP32 operations per instruction on a 64-bit register pair
-// (add / mul / fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2).  A cplx<float> IS such a pair, so complex
-// additions, subtractions and multiplications by a real scalar take one issue slot instead of two.
-// ncu (profiles/r1c_*): the single-precision sweeps are issue bound -- 70-83 % of their executed
-// instructions are the butterflies' FADD / FMUL / FFMA, 2.0-2.3 of 4 issue slots per cycle are
-// used, DRAM sits at 40-45 % -- so instruction count is what buys time.
-// MEASURED (profiles/r1d_f32x2_ab.txt): packing the butterflies' additions removed 17 % of the
-// D-sweeps' instructions (992 FADD -> 456 FADD2 + 144 FADD per tile and thread) and changed no
-// kernel's time by more than noise, the y sweep got 8 % slower: FADD2 holds the FMA pipe for two
-// issue cycles, and the sweeps are bound by their load -> transform -> store phase structure at
-// 16 resident warps per SM, not by issue slots.  Build option (-DGLIA_USE_F32X2), default off.
-#if !defined(GLIA_SIMT_EMU) && defined(GLIA_USE_F32X2)
-#define GLIA_F32X2 1
-__device__ __forceinline__ unsigned long long c_bits(cplx<float> v) { return *reinterpret_cast<unsigned long long*>(&v); }
-__device__ __forceinline__ cplx<float> c_from(unsigned long long u) { return *reinterpret_cast<cplx<float>*>(&u); }
-__device__ __forceinline__ cplx<float> cadd(cplx<float> a, cplx<float> b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(b)));
-  return c_from(r);
-}
-__device__ __forceinline__ cplx<float> csub(cplx<float> a, cplx<float> b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(b)));
-  return c_from(r);
-}
-// a * (s, s)
-__device__ __forceinline__ cplx<float> cscale(cplx<float> a, float s) {
-  unsigned long long r;
-  const cplx<float> ss = {s, s};
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c_bits(a)), "l"(c_bits(ss)));
-  return c_from(r);
-}
-#else
-#define GLIA_F32X2 0
-#endif
+// (Measured in round 1 and removed: Blackwell's packed FP32x2 adds for the butterflies' complex additions took 17 % of
+// the D-sweeps' instructions away and changed no kernel's time -- FADD2 holds the FMA pipe for two issue cycles,
+// profiles/r1d_f32x2_ab.txt.)
 template <typename T>
 __device__ __forceinline__ cplx<T> cscale(cplx<T> a, T s) { return {a.x * s, a.y * s}; }
 
-// ------------------------------------------------- L2 residency hints ----
-// At 256^3 single precision one field is 67 MB and B200's L2 holds 126 MB: of the fields a PCG
-// iteration touches, exactly one fits next to the streams.  With GLIA_L2_HINTS=1 the sweeps read
-// every operand that is consumed once per kernel (x, k, r, w, the last read of acc / shat) with the
-// evict-first policy (ld.global.cs), so that the field handed from one kernel to the next
-// (acc -> w -> shat -> z) survives in L2 until its consumer runs.
-// MEASURED (profiles/r1b_l2_probe.txt, profiles/r1c_l2_hints_ab.txt): a DRAM-bound 4F streaming
-// kernel gains 25-30% from this (7.5 TB/s effective against 5.5), but the sweep kernels do not --
-// they are issue / latency bound, not DRAM bound, at this size (65 us for 4F where DRAM needs 41) --
-// and evict-first STORES of sub-sector pieces (the z sweeps write 64-byte runs) tripled kz_r2c's
-// time.  Default OFF; kept as a build option for grids whose sweeps become DRAM bound.
-#ifndef GLIA_L2_HINTS
-#define GLIA_L2_HINTS 0
-#endif
-#if defined(GLIA_SIMT_EMU) || !GLIA_L2_HINTS
+// Loads of operands that are consumed once per kernel.  (Measured in round 1 and removed: evict-first loads /
+// stores -- ld.global.cs, st.global.cs -- and an access-policy window on the staged tiles gained nothing on the
+// sweeps, which are not DRAM bound at 256^3, and evict-first stores of 64-byte runs tripled kz_r2c's time;
+// profiles/r1b_l2_probe.txt, r1c_l2_hints_ab.txt.)
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return *p; }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { *p = v; }
-#else
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
-__device__ __forceinline__ cplx<float> ld_stream(const cplx<float>* p) {
-  const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
-  return {v.x, v.y};
-}
-__device__ __forceinline__ cplx<double> ld_stream(const cplx<double>* p) {
-  const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
-  return {v.x, v.y};
-}
-__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream(cplx<float>* p, cplx<float> v) {
-  __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
-}
-__device__ __forceinline__ void st_stream(cplx<double>* p, cplx<double> v) {
-  __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
-}
-#endif
 
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may
 // be scheduled while its predecessor's last CTAs are still draining; it does its set-up (indices,
 // twiddle registers from the constant per-axis table) and then waits here until the predecessor grid
 // has completed and its memory is visible.  Nothing produced by an earlier kernel may be touched
 // before this call.
-#ifndef GLIA_PDL_MODE
-// 0: no PDL instructions (probe builds), 1: wait only, 2: explicit early trigger + wait.  Measured: the explicit
-// griddepcontrol.launch_dependents on entry slows the multi-wave z sweeps (kz_deriv2 600 -> 629 us, kz_r2c.axpy
-// 473 -> 530 us at 512^3) and gains nothing over the implicit trigger at CTA exit (90.0 vs 88.5 time-steps/s at
-// 256^3), so the default is the wait alone.
-#define GLIA_PDL_MODE 1
-#endif
+// (Measured in round 1: an explicit griddepcontrol.launch_dependents on entry slows the multi-wave z sweeps by 5-12 %
+// at 512^3 and gains nothing over the implicit trigger at CTA exit, profiles/r1l_pdl_matrix.txt -- the wait alone.)
 __device__ __forceinline__ void pdl_wait() {
-#if !defined(GLIA_SIMT_EMU) && GLIA_PDL_MODE >= 1
-#if GLIA_PDL_MODE >= 2
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the NEXT kernel's CTAs fill our tail
-#endif
+#if !defined(GLIA_SIMT_EMU)
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
@@ -151,28 +79,6 @@ __device__ __forceinline__ void prefetch_l1(const V* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
   (void)p;
-#endif
-}
-
-#ifndef GLIA_TW_LDG
-#define GLIA_TW_LDG 0
-#endif
-// read-only load of a twiddle-table entry; volatile, because a plain __ldg is hoisted out of the transforms by
-// ptxas and the values sit in registers again
-template <typename T>
-__device__ __forceinline__ cplx<T> ld_table(const cplx<T>* p) {
-#if defined(GLIA_SIMT_EMU)
-  return *p;
-#else
-  if constexpr (sizeof(T) == 4) {
-    float x, y;
-    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
-    return {(T)x, (T)y};
-  } else {
-    double x, y;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
-    return {(T)x, (T)y};
-  }
 #endif
 }
 
@@ -229,30 +135,6 @@ __device__ __forceinline__ cplx<T> twmul_const(cplx<T> d) {
 }
 
 // --------------------------------------------- in-register radix-R DFT ----
-#if GLIA_F32X2
-template <typename T, int R, int SIGN, int J>
-__device__ __forceinline__ void dif_bf(cplx<T>* v) {
-  constexpr int H = R / 2;
-  constexpr int j32 = (J % R) * (32 / R);
-  cplx<T> a = v[J], b = v[J + H];
-  v[J] = cadd(a, b);
-  if constexpr (j32 == 8) {
-    // (a - b) * (SIGN i) written as two operand-swapped subtractions, so that no negation is needed
-    // (the packed add / sub results feed other packed operations, which take no sign modifiers in PTX)
-    if constexpr (SIGN > 0) v[J + H] = {b.y - a.y, a.x - b.x};
-    else v[J + H] = {a.y - b.y, b.x - a.x};
-  } else if constexpr (j32 == 0 || j32 == 16 || j32 == 24) {
-    v[J + H] = twmul_const<T, R, J, SIGN>(csub(a, b));
-  } else {
-    // d (c + i s) = (d.x c, d.y c) + (-s d.y, s d.x): one scaling of the pair + two FMAs
-    constexpr T c = (T)cos32(j32);
-    constexpr T s = (T)(SIGN * sin32(j32));
-    const cplx<T> d = csub(a, b);
-    const cplx<T> dc = cscale(d, c);
-    v[J + H] = {dc.x - s * d.y, dc.y + s * d.x};
-  }
-}
-#else
 template <typename T, int R, int SIGN, int J>
 __device__ __forceinline__ void dif_bf(cplx<T>* v) {
   constexpr int H = R / 2;
@@ -260,7 +142,6 @@ __device__ __forceinline__ void dif_bf(cplx<T>* v) {
   v[J] = cadd(a, b);
   v[J + H] = twmul_const<T, R, J, SIGN>(csub(a, b));
 }
-#endif
 template <typename T, int R, int SIGN, int... J>
 __device__ __forceinline__ void dif_level(cplx<T>* v, std::integer_sequence<int, J...>) {
   (dif_bf<T, R, SIGN, J>(v), ...);
@@ -322,16 +203,11 @@ struct LineFft {
     return n;
   }
   static constexpr int NTW = ntw() > 0 ? ntw() : 1;
-  // GLIA_TW_LDG (probe builds, default 0): three-pass plans (512-point lines) hold 28 complex inter-pass
-  // twiddles per thread.  Level 1 reads the pass-0 twiddles from the 4 KB per-axis table at the point of use
-  // (read-only path, L1-resident) instead of keeping them in registers; level 2 does so for every pass.
-  // Same table entries either way, so results are bit-identical.  ptxas evidence in DESIGN.md 6 (lever 1).
-  static constexpr int TWL = (P == 3) ? GLIA_TW_LDG : 0;
-  __host__ __device__ static constexpr bool tw_in_regs(int p) { return TWL == 0 || (TWL == 1 && p >= 1); }
+  // (Measured in round 2 and removed: reading the inter-pass twiddles of the three-pass 512-point plan from the per-axis
+  // table at the point of use instead of holding 28 complex registers -- no kernel gained, the 512^3 step lost 5 %,
+  // profiles/r2d_zpipe_twldg_ab.txt.)
   struct Tw {
     cplx<T> w[NTW];
-    const cplx<T>* table;
-    int t;
   };
 
   // location (natural position index at pass 0) of register (g, a) of pass p for thread t
@@ -355,8 +231,6 @@ struct LineFft {
 
   // table[j] = exp(-2 pi i j / N), j < N (built on the host in double)
   __device__ static __forceinline__ void load_twiddles(Tw& tw, const cplx<T>* __restrict__ table, int t) {
-    tw.table = table;
-    tw.t = t;
     int idx = 0;
     GLIA_UNROLL
     for (int p = 0; p + 1 < P; ++p) {
@@ -365,8 +239,7 @@ struct LineFft {
         const int b = (t + TPL * g) % Mp(p);
         GLIA_UNROLL
         for (int c = 1; c < R(p); ++c) {
-          if (tw_in_regs(p)) tw.w[idx] = table[(b * c * (N / Np(p))) % N];
-          ++idx;
+          tw.w[idx++] = table[(b * c * (N / Np(p))) % N];
         }
       }
     }
@@ -389,13 +262,7 @@ struct LineFft {
       for (int g = 0; g < Gp(p); ++g) {
         GLIA_UNROLL
         for (int c = 1; c < R(p); ++c) {
-          cplx<T> w;
-          if constexpr (tw_in_regs(p)) {
-            w = tw.w[twoff(p) + g * (R(p) - 1) + (c - 1)];
-          } else {
-            const int b = (tw.t + TPL * g) % Mp(p);
-            w = ld_table(tw.table + (b * c * (N / Np(p))) % N);
-          }
+          const cplx<T> w = tw.w[twoff(p) + g * (R(p) - 1) + (c - 1)];
           v[g * R(p) + c] = CONJ ? cmulc(v[g * R(p) + c], w) : cmul(v[g * R(p) + c], w);
         }
       }
@@ -433,9 +300,11 @@ struct LineFft {
       butterflies<2, -1>(v);
     }
   }
-  // frequencies (last-pass placement) -> natural positions, unnormalised
+  // frequencies (last-pass placement) -> natural positions, unnormalised.  Two halves, so that a kernel can put work
+  // between the last exchange (after which a thread's own natural positions of `sm` are read by nobody else) and
+  // the register-only final pass.
   template <class AM, class SY>
-  __device__ static __forceinline__ void inverse(cplx<T> (&v)[E], const Tw& tw, cplx<T>* sm, AM am, SY sync, int t) {
+  __device__ static __forceinline__ void inverse_head(cplx<T> (&v)[E], const Tw& tw, cplx<T>* sm, AM am, SY sync, int t) {
     if constexpr (P >= 3) {
       butterflies<2, +1>(v);
       exchange<2, 1>(v, sm, am, sync, t);
@@ -445,8 +314,15 @@ struct LineFft {
       butterflies<1, +1>(v);
       exchange<1, 0>(v, sm, am, sync, t);
     }
+  }
+  __device__ static __forceinline__ void inverse_tail(cplx<T> (&v)[E], const Tw& tw) {
     twiddle<0, true>(v, tw);
     butterflies<0, +1>(v);
+  }
+  template <class AM, class SY>
+  __device__ static __forceinline__ void inverse(cplx<T> (&v)[E], const Tw& tw, cplx<T>* sm, AM am, SY sync, int t) {
+    inverse_head(v, tw, sm, am, sync, t);
+    inverse_tail(v, tw);
   }
 
   // v <- (i * w(k) / N) v with the Nyquist wavenumber zeroed (trap T1;

@@ -20,30 +20,49 @@ enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_DIVERGED_ITS = -3, KS
 
 template <int NV>
 __device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int n, double (&out)[NV]) {
-  // fixed-order (deterministic) two-level sum by one CTA; the first min(blockDim, 256) threads gather
-  // with that stride (256 for the scalar kernels and the 256-thread sweeps), then a binary tree
-  __shared__ double sh[256 * NV];
-  const int tid = threadIdx.x, nt = (int)blockDim.x;
-  const int nth = nt < 256 ? nt : 256;
-  for (int j = tid; j < 256 * NV; j += nt) sh[j] = 0.0;
-  __syncthreads();
+  // Fixed-order (deterministic) sum by one CTA of 256 threads: thread t adds entries t, t + 256, ... in that order,
+  // a warp adds its lanes in a fixed butterfly, warp 0 adds the warps' sums in a fixed butterfly.  The loads of a
+  // thread are independent and issued eight at a time (one L2 round trip per batch, not per entry: this kernel sits
+  // on the critical path of every PCG iteration).
+  __shared__ double sh[8 * NV];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nth = 256;
+  double acc[NV];
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
   if (tid < nth) {
-    double acc[NV];
-    GLIA_UNROLL
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int j = tid; j < n; j += nth)
+    int j = tid;
+    for (; j + 7 * nth < n; j += 8 * nth) {
+      double v[8][NV];
+      GLIA_UNROLL
+      for (int u = 0; u < 8; ++u)
+        GLIA_UNROLL
+        for (int i = 0; i < NV; ++i) v[u][i] = partial[(size_t)(j + u * nth) * NV + i];
+      GLIA_UNROLL
+      for (int u = 0; u < 8; ++u)
+        GLIA_UNROLL
+        for (int i = 0; i < NV; ++i) acc[i] += v[u][i];
+    }
+    for (; j < n; j += nth)
       GLIA_UNROLL
       for (int i = 0; i < NV; ++i) acc[i] += partial[(size_t)j * NV + i];
-    GLIA_UNROLL
-    for (int i = 0; i < NV; ++i) sh[tid * NV + i] = acc[i];
+  }
+  GLIA_UNROLL
+  for (int i = 0; i < NV; ++i) {
+    double v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && wid < 8) sh[wid * NV + i] = v;
   }
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    for (int q = tid; q < s; q += nt)
-      GLIA_UNROLL
-      for (int i = 0; i < NV; ++i) sh[q * NV + i] += sh[(q + s) * NV + i];
-    __syncthreads();
+  if (wid == 0) {
+    GLIA_UNROLL
+    for (int i = 0; i < NV; ++i) {
+      double v = lane < 8 ? sh[lane * NV + i] : 0.0;
+      for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[i] = v;
+    }
   }
+  __syncthreads();
   GLIA_UNROLL
   for (int i = 0; i < NV; ++i) out[i] = sh[i];
   __syncthreads();
@@ -129,9 +148,12 @@ __global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, i
 // Runs iff iteration `it` really executed (it <= I_ITS): the converged iteration still
 // owes x its update (VecAXPY(X,a,P) precedes the test in KSPSolve_CG), a speculative
 // launch past convergence must do nothing.
+// `xin` is where the iterate lives before this update: x itself, or -- first iteration of an out-of-place solve --
+// the field the solve started from (the time loops solve from one history slot into the next, PdeOperators.cpp:
+// 284-300, so that no c_[i+1] / c_half_[i] / p_[i] copy is left).
 template <typename T>
-__global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const double* scal, const int* iscal,
-                            int it) {
+__global__ void k_cg_update(long n, const T* xin, T* x, T* p, const T* __restrict__ z, const double* scal,
+                            const int* iscal, int it) {
   pdl_wait();
   if (it > iscal[I_ITS]) return;
   const T a = (T)scal[S_A], b = (T)scal[S_B];
@@ -139,7 +161,7 @@ __global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const d
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const T pv = p[i];
-    x[i] = x[i] + a * pv;
+    x[i] = xin[i] + a * pv;
     if (!done) p[i] = z[i] + b * pv;
   }
 }
@@ -147,11 +169,12 @@ __global__ void k_cg_update(long n, T* x, T* p, const T* __restrict__ z, const d
 // ---- logistic reaction (src/pde/PdeOperators.cpp:140-190, 318-370) -----------
 // nonlinear: a = c/(1-c); c <- a f/(a f + 1), f = exp(rho dt); c <- 1 if a is inf.
 // `1.0 - c` and `a*f + 1.0` are double expressions in the reference (trap T6).
+// (cin may be c: in place; the time loop reads c_half_[i] and writes c_[i+1])
 template <typename T>
-__global__ void k_reaction(long n, T* c, const T* __restrict__ rho, T dt, T* c_half_out) {
+__global__ void k_reaction(long n, const T* cin, T* c, const T* __restrict__ rho, T dt, T* c_half_out) {
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const T cv = c[i];
+    const T cv = cin[i];
     if (c_half_out) c_half_out[i] = cv;
     const T factor = g_exp((T)(rho[i] * dt));
     const T alph = (T)((double)cv / (1.0 - (double)cv));
@@ -166,14 +189,14 @@ __global__ void k_reaction(long n, T* c, const T* __restrict__ rho, T dt, T* c_h
 }
 // linearised / adjoint: u <- u f / (c f + 1 - c)^2
 template <typename T>
-__global__ void k_reaction_lin(long n, T* u, const T* __restrict__ rho, const T* __restrict__ clin, T dt) {
+__global__ void k_reaction_lin(long n, const T* uin, T* u, const T* __restrict__ rho, const T* __restrict__ clin, T dt) {
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const T cv = clin[i];
     const T factor = g_exp((T)(rho[i] * dt));
     const T cf = cv * factor;
     const T alph = (T)(((double)cf + 1.0) - (double)cv);
-    const T uf = u[i] * factor;
+    const T uf = uin[i] * factor;
     u[i] = uf / (alph * alph);
   }
 }

@@ -28,35 +28,36 @@
   unsigned char* name = _glia_dyn_smem
 
 namespace simt {
-inline std::unordered_map<const void*, size_t>& smem_attr_cache() {
-  static std::unordered_map<const void*, size_t> m;
-  return m;
+// Kernels that want more than the 48 KB default of dynamic shared memory must opt in with
+// cudaFuncSetAttribute, once per (device, function): the attribute lives in the device's context.
+// One mutex and one map for every launch path -- handles on different host threads (ensemble
+// members) and on different devices launch concurrently.
+inline void opt_in_smem(const void* k, size_t smem) {
+  // opt in above 32 KB already: static __shared__ (reduction scratch) counts against the 48 KB default too
+  if (smem <= 32 * 1024) return;
+  struct Key {
+    int dev;
+    const void* fn;
+    bool operator==(const Key& o) const { return dev == o.dev && fn == o.fn; }
+  };
+  struct Hash {
+    size_t operator()(const Key& k) const { return std::hash<const void*>()(k.fn) * 31u + (size_t)k.dev; }
+  };
+  static std::mutex mu;
+  static std::unordered_map<Key, size_t, Hash> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(Key{dev, k});
+  if (it == cache.end() || it->second < smem) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cache[Key{dev, k}] = smem;
+  }
 }
 template <class... KA, class... A>
 inline void launch(void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
-  // opt in above 32 KB already: static __shared__ (reduction scratch) counts against the 48 KB default too
-  if (smem > 32 * 1024) {
-    static std::mutex mu;  // handles on different host threads (ensemble members) launch concurrently
-    std::lock_guard<std::mutex> lock(mu);
-    auto& m = smem_attr_cache();
-    auto it = m.find((const void*)k);
-    if (it == m.end() || it->second < smem) {
-      cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      m[(const void*)k] = smem;
-    }
-  }
+  opt_in_smem((const void*)k, smem);
   k<<<grid, block, smem, st>>>(static_cast<KA>(args)...);
-}
-inline void opt_in_smem(const void* k, size_t smem) {
-  if (smem <= 32 * 1024) return;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  auto& m = smem_attr_cache();
-  auto it = m.find(k);
-  if (it == m.end() || it->second < smem) {
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    m[k] = smem;
-  }
 }
 // programmatic dependent launch: the kernel may become resident (and run everything above its
 // pdl_wait()) while the previous kernel of the stream drains.  Only for kernels that call pdl_wait()
@@ -83,16 +84,7 @@ template <class... KA, class... A>
 inline void launch_streaming(const void* win, size_t bytes, void (*k)(KA...), dim3 grid, dim3 block, size_t smem,
                              cudaStream_t st, A... args) {
   if (!win || !bytes) return launch(k, grid, block, smem, st, args...);
-  if (smem > 32 * 1024) {  // same opt-in as launch()
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    auto& m = smem_attr_cache();
-    auto it = m.find((const void*)k);
-    if (it == m.end() || it->second < smem) {
-      cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      m[(const void*)k] = smem;
-    }
-  }
+  opt_in_smem((const void*)k, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

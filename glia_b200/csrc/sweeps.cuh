@@ -21,12 +21,9 @@
 namespace glia {
 
 // ------------------------------------------------------------ helpers ----
-// complex columns (lanes) per S tile: 16 = 128-byte rows in single precision.  GLIA_SL=8 (64-byte
-// rows, half-size CTAs, twice as many independent barrier groups per SM) is a build-time A/B option.
-#ifndef GLIA_SL
-#define GLIA_SL 16
-#endif
-static constexpr int SL = GLIA_SL;
+// complex columns (lanes) per S tile: 16 = 128-byte rows in single precision.  (Measured in round 1: 8 columns --
+// 64-byte rows, half-size CTAs -- made the x sweep 70 -> 90 us.)
+static constexpr int SL = 16;
 
 // occupancy hint of the S kernels: two resident CTAs per SM for single-precision tiles of <= 256 threads
 template <typename T, int N>

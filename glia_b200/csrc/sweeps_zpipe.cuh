@@ -1,14 +1,14 @@
 // sweeps_zpipe.cuh -- persistent, warp-private, LDGSTS-pipelined form of the z second-derivative
-// sweep (kz_deriv2, sweeps.cuh).  ROUND-2 CANDIDATE: correct on the emulator and through the C ABI,
-// NOT yet measured on a B200, therefore off by default (GLIA_RD_ZPIPE=1 selects it).
+// sweep; the default wherever a line pair fits one warp (kz_deriv2 of sweeps.cuh serves the rest).
 //
-// Why: kz_deriv2 puts the 64 scalar loads of a line pair's x and k in flight at once; at 512-point
-// lines that costs 168 registers = ONE 256-thread CTA per SM (8 warps) and 41 % of the copy peak
-// (DESIGN.md 6, next lever 1).  Here the x lines of the NEXT line-pair group ride into shared
-// memory on cp.async while the current group is transformed, k is sent towards L1 on entry of the
-// round and read at the point of use, and nothing but the 16 complex values of the transform lives
-// across it.  A line pair belongs to N/E <= 32 threads of one warp, which fetch exactly the bytes
-// they later read, so the whole pipeline needs __syncwarp only: no CTA barrier, warps drift freely.
+// kz_deriv2 puts the 64 scalar loads of a line pair's x and k in flight at once; at 512-point lines
+// that costs 168 registers = ONE 256-thread CTA per SM.  Here the x lines of the NEXT line-pair group
+// ride into shared memory on cp.async while the current group is transformed, k is sent towards L1 on
+// entry of the round and read at the point of use, and nothing but the 16 complex values of the
+// transform lives across it.  A line pair belongs to N/E <= 32 threads of one warp, which fetch exactly
+// the bytes they later read, so the whole pipeline needs __syncwarp only: no CTA barrier, warps drift.
+// Measured on the B200 (profiles/r2d_zpipe_twldg_ab.txt): 49.7 -> 45.8 us at 256^3, 603 -> 526 us at
+// 512^3 (f32).
 //
 //   smem per line pair = stage[0] | stage[1] (2N reals each) | exchange (zpad complex)
 #pragma once

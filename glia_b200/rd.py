@@ -78,14 +78,23 @@ class RDHandle:
             raise _capi.GliaRdError(self.lib.glia_rd_last_error(self._h).decode())
 
     def close(self, collective=True):
+        """Slab handles: every rank closes its mappings of the peers' arenas, all ranks meet, then each frees
+        its own (disconnect -> barrier -> free, include/glia_rd.h)."""
         if getattr(self, "_h", None):
             if collective and getattr(self, "nranks", 1) > 1 and self._all_gather is not None:
                 try:
-                    self._all_gather(b"bye")  # peers must stop touching this arena before it is freed
+                    self.lib.glia_rd_ipc_disconnect(self._h, -1)
+                    self._all_gather(b"bye")
                 except Exception:
                     pass
             self.lib.glia_rd_destroy(self._h)
             self._h = C.c_void_p()
+
+    def wait_stream(self, stream=None):
+        """Order work already enqueued on `stream` (a cudaStream_t address, a torch.cuda.Stream, or None for
+        the legacy default stream) in front of this handle's later work."""
+        s = getattr(stream, "cuda_stream", stream)
+        self._ck(self.lib.glia_rd_wait_stream(self._h, int(s) if s else None))
 
     def __del__(self):
         try:
@@ -158,7 +167,13 @@ class RDHandle:
         self._ck(self.lib.glia_rd_set_ksp_tolerances(self._h, rtol, abstol, dtol, int(maxit)))
 
     # -- L2a ------------------------------------------------------------------------
+    def set_splitting_order(self, order):
+        self._ck(self.lib.glia_rd_set_splitting_order(self._h, int(order)))
+
     def resize_history(self, nt, dt):
+        if self.nranks > 1:   # nobody may still map the old history arena when it is freed
+            self._ck(self.lib.glia_rd_ipc_disconnect(self._h, 1))
+            self._all_gather(b"resize")
         self._ck(self.lib.glia_rd_resize_history(self._h, int(nt), float(dt)))
         self.nt, self.dt = int(nt), float(dt)
         if self.nranks > 1:
@@ -193,12 +208,16 @@ class RDHandle:
         self._ck(self.lib.glia_rd_set_secondary_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(k1), float(k2),
                                                        float(k3)))
 
+    def set_two_snapshot(self, d0, obs0=None):
+        """two_time_points_: data at t = 0 and its observation mask (copied); d0 = None switches it off."""
+        self._ck(self.lib.glia_rd_set_two_snapshot(self._h, _ptr(d0), _ptr(obs0)))
+
     def objective_gradient(self, c0, d1, wm, gm, csf, obs=None, beta=0.0, g_c0=None):
-        """evaluateObjectiveAndGradient in field space -> dict(J, mismatch, reg, g6, its)."""
-        J, g, its = (C.c_double * 3)(), (C.c_double * 6)(), (C.c_int * 2)()
+        """evaluateObjectiveAndGradient in field space -> dict(J, mismatch, reg, mismatch0, g6, its)."""
+        J, g, its = (C.c_double * 4)(), (C.c_double * 6)(), (C.c_int * 2)()
         self._ck(self.lib.glia_rd_objective_gradient(self._h, _ptr(c0), _ptr(d1), _ptr(obs), float(beta), _ptr(wm),
                                                      _ptr(gm), _ptr(csf), J, _ptr(g_c0), g, its))
-        return dict(J=J[0], mismatch=J[1], reg=J[2], g6=np.array(list(g)), its=(its[0], its[1]))
+        return dict(J=J[0], mismatch=J[1], reg=J[2], mismatch0=J[3], g6=np.array(list(g)), its=(its[0], its[1]))
 
     def hessian_matvec(self, c0_tilde, y_c0, wm, gm, csf, obs=None, beta=0.0, diffusivity_inversion=False):
         """evaluateHessian in field space -> (hk[6], ksp_its[4]); y_c0 is filled."""

@@ -14,7 +14,13 @@
  *     (precision 8) in the PETSc-Vec layout of the reference: C order [n0][n1][n2], z
  *     fastest (src/mat/DiffCoef.cpp:150); they stay owned by the caller;
  *   - calls are enqueued on the handle's stream and are synchronous at return;
- *   - a handle is not thread-safe; one handle per (process, device).
+ *   - the handle's stream is NON-BLOCKING: it has no implicit ordering with the legacy default
+ *     stream.  Input fields must be complete when a call is made -- synchronise their producer, or
+ *     order it in front of the library's work with glia_rd_wait_stream();
+ *   - a handle is not thread-safe (one call at a time), but it may be used from any host thread:
+ *     every entry point makes the handle's CUDA device current for the calling thread;
+ *   - slab handles: create / resize_history / destroy are collective and must follow the
+ *     disconnect -> barrier -> free order described at glia_rd_ipc_disconnect().
  */
 #ifndef GLIA_RD_H
 #define GLIA_RD_H
@@ -61,8 +67,18 @@ int glia_rd_create_slab(glia_rd_t** h, const int n[3], int precision, int device
 int glia_rd_ipc_export(glia_rd_t* h, int which, void* handle64);
 /* handles: nranks * 64 bytes in rank order (the all-gathered exports) */
 int glia_rd_ipc_connect(glia_rd_t* h, int which, const void* handles);
+/* Closes this rank's mappings of the peers' arenas (which: 0 = work arena, 1 = time histories, -1 = both).
+ * CUDA leaves freeing an exported allocation that another process still has open undefined, so teardown
+ * and every re-allocation of the histories are
+ *     every rank: glia_rd_ipc_disconnect  ->  caller-side barrier  ->  glia_rd_destroy / glia_rd_resize_history
+ * (the reference's AccFFT / PETSc objects are collective in the same way: accfft_destroy_plan, VecDestroy). */
+int glia_rd_ipc_disconnect(glia_rd_t* h, int which);
 int glia_rd_destroy(glia_rd_t* h);
 const char* glia_rd_last_error(const glia_rd_t* h);
+/* Orders everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the legacy default stream)
+ * in front of the handle's later work, without a host or device-wide synchronisation -- what the reference got
+ * for free from default-stream semantics. */
+int glia_rd_wait_stream(glia_rd_t* h, void* producer_stream);
 /* the CUDA stream (cudaStream_t) all work of this handle is enqueued on */
 void* glia_rd_stream(glia_rd_t* h);
 /* number of kernel launches issued by this handle since creation */
@@ -126,6 +142,9 @@ int glia_rd_set_ksp_tolerances(glia_rd_t* h, double rtol, double abstol, double 
  * (nt+1) state + (nt+1) adjoint + nt half-step fields, zero-initialised. */
 int glia_rd_resize_history(glia_rd_t* h, int nt, double dt);
 int glia_rd_history(glia_rd_t* h, int which, int i, void** dev_ptr);
+/* params->tu_->order_ (PdeOperators.cpp:271-290, 389-398): 2 = Strang splitting (default; half diffusion,
+ * reaction, half diffusion), 1 = full-dt diffusion then reaction, in solve_state and solve_adjoint. */
+int glia_rd_set_splitting_order(glia_rd_t* h, int order);
 /* PdeOperatorsRD::reaction (PdeOperators.cpp:140-190): c_lin == NULL -> nonlinear
  * logistic step, else the linearised step about c_lin. */
 int glia_rd_reaction(glia_rd_t* h, void* c_t, const void* c_lin, double dt);
@@ -154,13 +173,18 @@ int glia_rd_grad_kappa_rho(glia_rd_t* h, const void* wm, const void* gm, const v
  * (the caller resolves the nk == 1 ratios). */
 int glia_rd_set_secondary_tissue(glia_rd_t* h, const void* wm, const void* gm, const void* csf, double k1, double k2,
                                  double k3);
+/* params->tu_->two_time_points_ (DerivativeOperatorsRD.cpp:30-34, 149-153, 216-222): data d0 at t = 0 with its
+ * own observation mask (Obs::filter_0_, src/mat/Obs.cpp:60-100; NULL = identity).  Both fields are copied;
+ * d0 == NULL switches the two-snapshot terms off again.  While on, glia_rd_hessian_matvec fails like the
+ * reference's evaluateHessian does ("not implemented for two-snapshot scenario", :234). */
+int glia_rd_set_two_snapshot(glia_rd_t* h, const void* d0, const void* obs0);
 /* evaluateObjectiveAndGradient (DerivativeOperatorsRD.cpp:130-226): solveState(0), mismatch,
  * p_T = -O^T(O c(1) - d1), solveAdjoint(1), gradDiffusion + gradReaction.
- *   J[3]   = { J, h^3/2 ||O c(1) - d1||^2, beta/2 h^3 ||c0||^2 }
- *   g_c0   = -h^3 (alpha(0) - beta c0)          (device field, may be NULL)
+ *   J[4]   = { J, h^3/2 ||O c(1) - d1||^2, beta/2 h^3 ||c0||^2, h^3/2 ||O0 c(0) - d0||^2 (0 unless two-snapshot) }
+ *   g_c0   = -h^3 (alpha(0) - beta c0) [+ h^3 O0^T (O0 c0 - d0)]     (device field, may be NULL)
  *   g[6]   = as glia_rd_grad_kappa_rho;  ksp_its[2] = { state, adjoint } iteration totals. */
 int glia_rd_objective_gradient(glia_rd_t* h, const void* c0, const void* d1, const void* obs, double beta,
-                               const void* wm, const void* gm, const void* csf, double J[3], void* g_c0, double g[6],
+                               const void* wm, const void* gm, const void* csf, double J[4], void* g_c0, double g[6],
                                int ksp_its[2]);
 /* evaluateHessian (DerivativeOperatorsRD.cpp:229-438), Gauss-Newton product about the state of
  * the last objective_gradient call.  c0_tilde = Phi p~.  diffusivity_inversion = 0: y_c0 =

@@ -345,7 +345,7 @@ class DerivativeOperatorsRD {
   // c(0) = tumor_->c_0_ (= Phi p), data d1; dJ_field = -h^3 (alpha(0) - beta c0) (g_p = Phi^T dJ_field);
   // g_kappa[nk], g_rho[nr] as gradDiffusion / gradReaction assemble them.
   ErrorCode evaluateObjectiveAndGradient(double* J, Vec<Real>& dJ_field, double* g_kappa, double* g_rho, const Vec<Real>& d1) {
-    double Jv[3], g6[6];
+    double Jv[4], g6[6];   // J, D(c1), S(c0), D(c0) -- the last one 0 unless setTwoSnapshot()
     int its[2];
     ErrorCode e = glia_rd_objective_gradient(spec_ops_->handle(), tumor_->c_0_.array(), d1.array(), obs_ ? obs_->array() : nullptr,
                                              params_->beta, mat_prop_->wm_->array(), mat_prop_->gm_->array(),
@@ -356,6 +356,11 @@ class DerivativeOperatorsRD {
     pde_->diff_ksp_itr_state_ = its[0];
     pde_->diff_ksp_itr_adj_ = its[1];
     return 0;
+  }
+  // params_->tu_->two_time_points_ with Data::dt0() and Obs::filter_0_ (DerivativeOperatorsRD.cpp:30-34, 149-153,
+  // 216-222); obs0 == nullptr is O0 = I, d0 == nullptr switches the terms off
+  ErrorCode setTwoSnapshot(const Vec<Real>* d0, const Vec<Real>* obs0 = nullptr) {
+    return glia_rd_set_two_snapshot(spec_ops_->handle(), d0 ? d0->array() : nullptr, obs0 ? obs0->array() : nullptr);
   }
   // evaluateHessian(y, x) in field space (DerivativeOperatorsRD.cpp:229-438): x = (c0~ = Phi p~, k~);
   // y_field as above, y_kappa[nk] = Hkp p~ + Hkk k~ when diffusivity_inversion is set.

@@ -428,7 +428,8 @@ class PdeOperatorsRD:
     src/pde/PdeOperators.cpp:140-420."""
 
     def __init__(self, k: DiffCoef, rho: np.ndarray, nt: int, dt: float,
-                 dt_ctx=None, adjoint_store=True):
+                 dt_ctx=None, adjoint_store=True, order=2):
+        self.order = int(order)     # params->tu_->order_ (PdeOperators.cpp:271-290, 389-398)
         self.k = k
         self.rho = rho
         self.nt = int(nt)
@@ -463,7 +464,7 @@ class PdeOperatorsRD:
         for i in range(nt):
             if linearized == 2:
                 c = self.solve_incremental(c, i, 1, dt / 2)
-            c = self.diff.solve(c, dt / 2.0)
+            c = self.diff.solve(c, dt / 2.0 if self.order == 2 else dt)
             self.ksp_state += self.diff.ksp_itr
             self.ksp_trace.append(self.diff.ksp_itr)
             if linearized == 0 and self.adjoint_store:
@@ -472,11 +473,12 @@ class PdeOperatorsRD:
                 c = reaction_nonlinear(c, self.rho, dt)
             else:
                 c = reaction_linearized(c, self.c_[i], self.rho, dt)
-            c = self.diff.solve(c, dt / 2.0)
-            self.ksp_state += self.diff.ksp_itr
-            self.ksp_trace.append(self.diff.ksp_itr)
-            if linearized == 2:
-                c = self.solve_incremental(c, i, 2, dt / 2)
+            if self.order == 2:
+                c = self.diff.solve(c, dt / 2.0)
+                self.ksp_state += self.diff.ksp_itr
+                self.ksp_trace.append(self.diff.ksp_itr)
+                if linearized == 2:
+                    c = self.solve_incremental(c, i, 2, dt / 2)
             if linearized == 0:
                 self.c_[i + 1] = c.copy()
         return c
@@ -490,7 +492,7 @@ class PdeOperatorsRD:
             self.p_[nt] = p.copy()
         self.ksp_adj = 0
         for i in range(nt):
-            p = self.diff.solve(p, dt / 2.0)
+            p = self.diff.solve(p, dt / 2.0 if self.order == 2 else dt)
             self.ksp_adj += self.diff.ksp_itr
             self.ksp_trace.append(self.diff.ksp_itr)
             it = nt - i - 1
@@ -500,9 +502,10 @@ class PdeOperatorsRD:
                 c_lin = self.diff.solve(self.c_[it].copy(), dt / 2.0)
                 self.ksp_adj += self.diff.ksp_itr
             p = reaction_linearized(p, c_lin, self.rho, dt)
-            p = self.diff.solve(p, dt / 2.0)
-            self.ksp_adj += self.diff.ksp_itr
-            self.ksp_trace.append(self.diff.ksp_itr)
+            if self.order == 2:
+                p = self.diff.solve(p, dt / 2.0)
+                self.ksp_adj += self.diff.ksp_itr
+                self.ksp_trace.append(self.diff.ksp_itr)
             self.p_[it] = p.copy()
         return p
 
@@ -555,9 +558,11 @@ class DerivativeOperatorsRD:
     (src/mat/Obs.cpp:75-140); obs = None is O = I.  L2 regularisation
     (:36-39).  The kappa / rho blocks are the six scalars of grad_kappa_rho."""
 
-    def __init__(self, pde: PdeOperatorsRD, wm, gm, csf, obs=None, beta=0.0):
+    def __init__(self, pde: PdeOperatorsRD, wm, gm, csf, obs=None, beta=0.0, d0=None, obs0=None):
         self.pde, self.wm, self.gm, self.csf = pde, wm, gm, csf
         self.obs = obs
+        # two_time_points_ (DerivativeOperatorsRD.cpp:30-34, 149-153, 216-222): data and mask at t = 0
+        self.d0, self.obs0 = d0, obs0
         self.beta = float(beta)
         n0, n1, n2 = pde.k.shape
         self.leb = (2 * np.pi / n0) * (2 * np.pi / n1) * (2 * np.pi / n2)
@@ -579,23 +584,33 @@ class DerivativeOperatorsRD:
         g_c0 = -h^3 (alpha(0) - beta c0), g6 = grad_kappa_rho (:130-226)."""
         d = DiffusionSolver._dot
         pde = self.pde
+        m0, t0 = 0.0, None
+        if self.d0 is not None:        # Oc(0) - d0 with the t = 0 mask (:149-153)
+            t0 = c0 if self.obs0 is None else (c0 * self.obs0).astype(self.dtype)
+            t0 = (t0 - self.d0).astype(self.dtype)
+            m0 = d(t0, t0)
         cT = pde.solve_state(c0, 0)
         temp, pT = self._terminal(cT, d1)
         m1 = d(temp, temp)
         reg = 0.5 * self.beta * d(c0, c0) * self.leb
-        J = self.leb * 0.5 * m1 + reg
+        J = self.leb * 0.5 * (m1 + m0) + reg
         p0 = pde.solve_adjoint(pT, 1)
         t = self.dtype.type
         g_c0 = ((p0 - t(self.beta) * c0).astype(self.dtype) * t(-self.leb)).astype(self.dtype)
+        if t0 is not None:             # + h^3 O0^T(O0 c0 - d0)  (:216-222, Phi^T factored out)
+            q = t0 if self.obs0 is None else (t0 * self.obs0).astype(self.dtype)
+            g_c0 = (g_c0 + t(self.leb) * q).astype(self.dtype)
         g6 = grad_kappa_rho(pde, self.wm, self.gm, self.csf)
-        return dict(J=J, mismatch=self.leb * 0.5 * m1, reg=reg, cT=cT, p0=p0, g_c0=g_c0, g6=g6,
-                    its=(pde.ksp_state, pde.ksp_adj))
+        return dict(J=J, mismatch=self.leb * 0.5 * m1, mismatch0=self.leb * 0.5 * m0, reg=reg, cT=cT, p0=p0,
+                    g_c0=g_c0, g6=g6, its=(pde.ksp_state, pde.ksp_adj))
 
     def evaluate_hessian(self, c0_tilde, diffusivity_inversion=False):
         """Gauss-Newton Hessian product (:229-438).  Needs the state history of a previous
         evaluate_objective_and_gradient (c_, c_half_; p_[nt] is the stale gradient adjoint, trap
         T4).  With diffusivity_inversion the secondary coefficients (k.set_secondary) carry
         k~.  -> (y_c0 field, hk[6] = h^3 <wm|gm|csf, T_kp>, h^3 <wm|gm|csf, T_kk>)."""
+        if self.d0 is not None:
+            raise NotImplementedError("Hessian currently not implemented for two-snapshot scenario")  # :234
         pde = self.pde
         t = self.dtype.type
         d = DiffusionSolver._dot

@@ -156,9 +156,10 @@ def reaction_linearized(u, c_lin, rho, dt):
 class PdeOperatorsRD:
     """src/pde/PdeOperators.cpp:235-420 (state + adjoint with c_half_ storage)."""
 
-    def __init__(self, k, kavg, k_scale, rho, nt, dt):
+    def __init__(self, k, kavg, k_scale, rho, nt, dt, dt_ctx=None):
         self.spec = SpectralOps(k.shape, k.dtype)
-        self.diff = DiffusionSolver(k, kavg, k_scale, dt, self.spec)
+        # dt_ctx: the solver context's time step when precFactor() ran (trap T2; default = dt as at construction)
+        self.diff = DiffusionSolver(k, kavg, k_scale, dt if dt_ctx is None else dt_ctx, self.spec)
         self.rho, self.nt, self.dt = rho, int(nt), float(dt)
         self.c_ = [None] * (nt + 1)
         self.p_ = [None] * (nt + 1)
@@ -194,9 +195,9 @@ class PdeOperatorsRD:
         return p
 
 
-def forward_adjoint(k, kavg, k_scale, rho, c0, d1, nt, dt):
+def forward_adjoint(k, kavg, k_scale, rho, c0, d1, nt, dt, dt_ctx=None):
     """One solveState(0) + terminal condition -(c(T) - d1) + solveAdjoint(1)."""
-    pde = PdeOperatorsRD(k, kavg, k_scale, rho, nt, dt)
+    pde = PdeOperatorsRD(k, kavg, k_scale, rho, nt, dt, dt_ctx)
     cT = pde.solve_state(c0)
     p0 = pde.solve_adjoint(-(cT - d1))
     return cT, p0, pde

@@ -222,17 +222,19 @@ def setup_handle(B, P, n, dtype, nt, dt):
     return h, dev
 
 
-def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_grad=True):
-    """solveState(0) -> p_T = -(c(T) - d) -> solveAdjoint(1) -> kappa/rho gradient integrals."""
+def case_forward_adjoint(B, n, dtype, nt=3, dt=0.04, adjoint_store=True, with_grad=True, order=2):
+    """solveState(0) -> p_T = -(c(T) - d) -> solveAdjoint(1) -> kappa/rho gradient integrals.
+    order = 1: the first-order splitting branch of solveState / solveAdjoint (PdeOperators.cpp:284-290, 395-398)."""
     sh = shape3(n)
     P = make_problem(n, dtype)
-    pde = O.PdeOperatorsRD(P["k"], P["rho"], nt, dt, dt_ctx=dt, adjoint_store=adjoint_store)
+    pde = O.PdeOperatorsRD(P["k"], P["rho"], nt, dt, dt_ctx=dt, adjoint_store=adjoint_store, order=order)
     cT_ref = pde.solve_state(P["c0"], 0)
     d1 = (0.9 * cT_ref + 0.05 * P["c0"]).astype(dtype)
     pT = (-(cT_ref - d1)).astype(dtype)
     p0_ref = pde.solve_adjoint(pT, 1)
 
     h, dev = setup_handle(B, P, n, dtype, nt, dt)
+    h.set_splitting_order(order)
     cT = B.empty(sh, dtype)
     its_s = h.solve_state(B.put(P["c0"]), cT, 0)
     res = {"its_state": (its_s, pde.ksp_state), "cT": rel(B.get(cT), cT_ref)}
@@ -360,6 +362,43 @@ def case_objective_hessian(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
     y2_ref, _, _ = D.evaluate_hessian(c0t, False)
     h.hessian_matvec(B.put(c0t), y, dev["wm"], dev["gm"], dev["csf"], obs=obs_d, beta=beta, diffusivity_inversion=False)
     res["h_y_ponly"] = rel(B.get(y), y2_ref)
+    h.close()
+    return res
+
+
+def case_two_snapshot(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
+    """two_time_points_ (DerivativeOperatorsRD.cpp:30-34, 149-153, 216-222): the t = 0 mismatch term of the
+    objective and its gradient contribution, with a t = 0 observation mask of its own; the Hessian refuses."""
+    sh = shape3(n)
+    P = make_problem(n, dtype)
+    pde = O.PdeOperatorsRD(P["k"], P["rho"], nt, dt, dt_ctx=dt)
+    obs1 = (P["wm"] > 0.2).astype(dtype)
+    obs0 = (P["wm"] > 0.35).astype(dtype)
+    d1 = (0.7 * P["c0"]).astype(dtype)
+    d0 = (0.9 * P["c0"] * P["wm"]).astype(dtype)
+    D = O.DerivativeOperatorsRD(pde, P["wm"], P["gm"], P["csf"], obs=obs1, beta=beta, d0=d0, obs0=obs0)
+    ref = D.evaluate_objective_and_gradient(P["c0"], d1)
+    h, dev = setup_handle(B, P, n, dtype, nt, dt)
+    gc0 = B.empty(sh, dtype)
+    h.set_two_snapshot(B.put(d0), B.put(obs0))
+    out = h.objective_gradient(B.put(P["c0"]), B.put(d1), dev["wm"], dev["gm"], dev["csf"], obs=B.put(obs1), beta=beta,
+                               g_c0=gc0)
+    res = {"J": abs(out["J"] - ref["J"]) / abs(ref["J"]),
+           "m0": abs(out["mismatch0"] - ref["mismatch0"]) / abs(ref["mismatch0"]),
+           "m0_share": ref["mismatch0"] / ref["J"], "g_c0": rel(B.get(gc0), ref["g_c0"])}
+    from glia_b200._capi import GliaRdError
+    try:
+        h.hessian_matvec(B.put(P["c0"]), gc0, dev["wm"], dev["gm"], dev["csf"], beta=beta)
+        res["hessian_refused"] = False
+    except GliaRdError as e:
+        res["hessian_refused"] = "two-snapshot" in str(e)
+    # off again: the one-snapshot objective
+    h.set_two_snapshot(None)
+    D1 = O.DerivativeOperatorsRD(pde, P["wm"], P["gm"], P["csf"], obs=obs1, beta=beta)
+    ref1 = D1.evaluate_objective_and_gradient(P["c0"], d1)
+    out1 = h.objective_gradient(B.put(P["c0"]), B.put(d1), dev["wm"], dev["gm"], dev["csf"], obs=B.put(obs1), beta=beta)
+    res["J_off"] = abs(out1["J"] - ref1["J"]) / abs(ref1["J"])
+    res["m0_off"] = out1["mismatch0"]
     h.close()
     return res
 

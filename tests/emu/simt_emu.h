@@ -9,7 +9,11 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
 #include <barrier>
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <string>
@@ -183,6 +187,7 @@ struct Fork {
   void end(cudaStream_t) {}
 };
 inline void stream_destroy(cudaStream_t) {}
+inline int stream_wait_stream(cudaStream_t, cudaStream_t) { return 0; }
 inline const char* err_string(int) { return "emu"; }
 struct Profiler {
   bool on = false;

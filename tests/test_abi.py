@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
         assert hasattr(lib, name), name
     lib.glia_rd_build_info.restype = C.c_char_p
     assert lib.glia_rd_build_info() == b"cuda-sm_100a"
-    assert lib.glia_rd_abi_version() == 1
+    assert lib.glia_rd_abi_version() == 2
 
 
 def test_no_cpu_fallback(cuda_lib):

@@ -333,15 +333,56 @@ def test_reference_pins_K2_K3_on_the_gpu(B, which, dtype):
     assert err < Cs.TOL[np.dtype(dtype)], err
 
 
-def test_two_sequence_packed_sweeps_match(B, monkeypatch):
-    """GLIA_RD_V2=1 selects the two-sequence packed FP32x2 D-sweeps (sweeps_v2.cuh; an A/B option,
-    slower than the default at 256^3): same parity bar as the default path."""
-    monkeypatch.setenv("GLIA_RD_V2", "1")
-    r = Cs.case_forward_adjoint(B, 64, np.float32, nt=2, dt=0.04)
-    assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1]
-    assert r["cT"] < 1e-5 and r["p0"] < 1e-5
-    e1, e2, budget = Cs.case_apply_D(B, 128, np.float32, False)
-    assert e1 < budget and e2 < budget
+def test_first_order_splitting(B):
+    """params->tu_->order_ != 2 (PdeOperators.cpp:284-290, 395-398) through solve_state / solve_adjoint."""
+    for dtype in DT:
+        r = Cs.case_forward_adjoint(B, 64, dtype, nt=3, dt=0.04, order=1)
+        tol = Cs.TOL[np.dtype(dtype)]
+        assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], r
+        assert r["cT"] < tol and r["p0"] < tol and r["grad"] < 10 * tol, r
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_two_snapshot_objective(B, dtype):
+    """two_time_points_: J and its c(0) gradient carry the t = 0 mismatch (DerivativeOperatorsRD.cpp:30-34,
+    149-153, 216-222); evaluateHessian refuses, as in the reference (:234)."""
+    r = Cs.case_two_snapshot(B, 64, dtype, nt=2)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["m0_share"] > 1e-3, r
+    assert r["J"] < 10 * tol and r["m0"] < 10 * tol and r["g_c0"] < 10 * tol, r
+    assert r["hessian_refused"] is True, r
+    assert r["J_off"] < 10 * tol and r["m0_off"] == 0.0, r
+
+
+def test_headline_size_one_time_step_vs_oracle(B):
+    """256^3, single precision (BASELINE config 2's grid): one Strang time step forward + adjoint + the kappa / rho
+    gradient against the CPU oracle, with EQUAL PCG iteration counts -- the m_i that set the roofline bytes of the
+    bench are the oracle's.  ~1 min of CPU for the oracle."""
+    r = Cs.case_forward_adjoint(B, 256, np.float32, nt=1, dt=0.04)
+    assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], r
+    assert r["cT"] < 1e-5 and r["p0"] < 1e-5 and r["grad"] < 1e-4, (r["cT"], r["p0"], r["grad"], r["grad_vals"])
+
+
+def test_wait_stream_orders_a_producer(B):
+    """glia_rd_wait_stream: a field produced on another (torch) stream is ordered in front of the library's work
+    without a device-wide synchronisation."""
+    torch = B.torch
+    n = 128
+    h = B.handle(n, np.float32)
+    side = torch.cuda.Stream()
+    x = torch.zeros((n, n, n), dtype=torch.float32, device=B.dev)
+    gz = torch.empty_like(x)
+    torch.cuda.synchronize()
+    ax = torch.arange(n, device=B.dev, dtype=torch.float32) * (2 * np.pi / n)
+    with torch.cuda.stream(side):
+        for _ in range(20):           # keep the producer busy for a while
+            x.copy_(torch.sin(3 * ax)[None, None, :].expand(n, n, n))
+    h.wait_stream(side)
+    h.gradient(None, None, gz, x, 4)
+    torch.cuda.synchronize()
+    ref = (3 * torch.cos(3 * ax))[None, None, :].expand(n, n, n)
+    assert float((gz - ref).abs().max()) < 1e-4
+    h.close()
 
 
 def test_netcdf_round_trip_and_label_split_on_device(B, tmp_path):

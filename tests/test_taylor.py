@@ -221,7 +221,6 @@ def test_gpu_gradient_taylor(cuda_lib, torch_cuda):
         assert abs(Jg - J0) < 1e-10 * abs(J0)
         assert Cs.rel(g_c0g, g_c0) < 1e-9
         assert abs(gkg - gk) < 1e-8 * abs(gk) and abs(grg - gr) < 1e-8 * abs(gr)
-        assert out["J0"] == Jg
     finally:
         M.close()
 
