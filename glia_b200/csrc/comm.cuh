@@ -94,6 +94,69 @@ __device__ inline void peer_signal_wait(const Comm& c, unsigned epoch, int t) {
   }
 }
 
+// Rank gate folded into a kernel (the slab x sweeps and the kernels that consume their results), so that the hot
+// loop needs no stand-alone k_peer_barrier launches (13 us each, 4 per PCG iteration in round 1):
+//   entry  -- CTA 0 announces `signal_in` to every peer (everything this rank enqueued before the kernel is complete:
+//             the kernel is launched without the programmatic-launch attribute, or has passed its pdl_wait);
+//             every CTA then waits until every peer has announced `wait_epoch`;
+//   exit   -- the last CTA of the grid to finish (ticket counter) announces `signal_out`: all of this rank's writes
+//             into the peers' memory are complete and visible.
+// All three are optional (epoch 0 = none); G <= 1 makes the gate a no-op.
+struct PeerGate {
+  Comm comm;
+  unsigned signal_in = 0, wait_epoch = 0, signal_out = 0;
+  unsigned* ticket = nullptr;  // device counter, zero between uses
+};
+// all threads of the CTA call this once, before touching peer-written or peer-read data
+__device__ inline void gate_enter(const PeerGate& g) {
+  if (g.comm.G <= 1) return;
+  const int t = threadIdx.x;
+  if (g.signal_in && blockIdx.x == 0 && t < g.comm.G) {
+    fence_sys();
+    st_release_sys(g.comm.flags[t] + g.comm.rank, g.signal_in);
+  }
+  if (g.wait_epoch && t < g.comm.G) {
+    const unsigned* mine = g.comm.flags[g.comm.rank] + t;
+    unsigned long long t0 = 0;
+    unsigned polls = 0;
+    while ((int)(ld_acquire_sys(mine) - g.wait_epoch) < 0) {
+      spin_pause();
+      if ((++polls & 1023u) == 0) {
+        const unsigned long long now = now_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > g.comm.timeout_ns) {
+          *g.comm.err = 1;
+          if (g.comm.done) *g.comm.done = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+// all threads of the CTA call this once, after their last store
+__device__ inline void gate_exit(const PeerGate& g) {
+  if (g.comm.G <= 1 || !g.signal_out) return;
+  __syncthreads();  // every thread's stores precede thread 0's fence (the grid-sync pattern)
+  if (threadIdx.x == 0) {
+    fence_sys();
+#if defined(GLIA_SIMT_EMU)
+    const unsigned prev = std::atomic_ref<unsigned>(*g.ticket).fetch_add(1u, std::memory_order_acq_rel);
+#else
+    const unsigned prev = atomicAdd(g.ticket, 1u);
+#endif
+    if (prev == gridDim.x - 1) {
+      fence_sys();
+      *g.ticket = 0;
+      fence_sys();
+      for (int q = 0; q < g.comm.G; ++q) st_release_sys(g.comm.flags[q] + g.comm.rank, g.signal_out);
+    }
+  }
+}
+
+// stand-alone consumer side of a gate, for the kernels that carry none (one-tile-per-CTA fallbacks)
+static __global__ void k_gate_wait(PeerGate g) { gate_enter(g); }
+
 // all ranks: everything enqueued before the barrier on every rank is complete and visible
 static __global__ void k_peer_barrier(Comm c, unsigned epoch) {
   const int t = threadIdx.x;

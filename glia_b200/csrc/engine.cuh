@@ -17,6 +17,7 @@
 #include "sweeps_dist.cuh"
 #include "sweeps_pipe.cuh"
 #include "sweeps_zpipe.cuh"
+#include "sweeps_tma.cuh"
 
 namespace glia {
 
@@ -206,6 +207,8 @@ class Engine : public EngineBase {
   bool hist_connected = false;
   Comm comm;
   unsigned epoch = 0, rseq = 0;
+  unsigned* ticket = nullptr;   // device counter of the in-kernel rank gates (PeerGate)
+  unsigned gate_pending = 0;    // epoch the last gated x sweep announces on exit; its consumer waits for it
   int nsm = 148;         // SMs of this device: grid size of the persistent (pipelined) sweeps
   // slab D-apply: run the rank-local z sweep on a side stream (into acc2) WHILE the peer x sweep, which is
   // NVLink-bound and leaves SM time unused, runs on a share of the SMs; the y sweep then takes acc + acc2
@@ -283,6 +286,9 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::stream_create(&st));
     nsm = rt::sm_count(device);
     if (const char* e = std::getenv("GLIA_RD_PDL")) use_pdl = std::atoi(e) != 0;
+#if !defined(GLIA_SIMT_EMU)
+    if (const char* e = std::getenv("GLIA_RD_TMA")) use_tma = std::atoi(e) != 0 && nranks_ == 1;
+#endif
     if (const char* e = std::getenv("GLIA_RD_PDL_SLAB")) use_pdl_slab = std::atoi(e) != 0;
     if (const char* e = std::getenv("GLIA_RD_DIST_DEBUG")) dist_debug = std::atoi(e);
     if (const char* e = std::getenv("GLIA_RD_XZ")) use_xz = std::atoi(e) != 0;
@@ -326,6 +332,8 @@ class Engine : public EngineBase {
     GLIA_CHECK(rt::dev_malloc((void**)&partial, sizeof(double) * npart * 3));
     GLIA_CHECK(rt::dev_malloc((void**)&scal, sizeof(double) * S_NSCAL));
     GLIA_CHECK(rt::dev_malloc((void**)&iscal, sizeof(int) * I_NISCAL));
+    GLIA_CHECK(rt::dev_malloc((void**)&ticket, sizeof(unsigned) * 4));
+    GLIA_CHECK(rt::zero(ticket, sizeof(unsigned) * 4, st));
     GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL, st));
     GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL, st));
     comm.err = iscal + I_COMM_ERR;
@@ -351,7 +359,7 @@ class Engine : public EngineBase {
     if (G > 1) { rt::ipc_free(arena, arena_bytes, arena_handle); rt::ipc_free(hist_arena, hist_bytes, hist_handle); }
     else { rt::dev_free(arena); rt::dev_free(hist_arena); }
     for (int a = 0; a < 3; ++a) rt::dev_free(tw[a]);
-    rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal);
+    rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal); rt::dev_free(ticket);
     rt::host_free(h_iscal); rt::host_free(h_out);
     rt::host_free(hs_in); rt::host_free(hs_out);
     for (int a = 0; a < 3; ++a) rt::dev_free(symtab[a]);
@@ -441,6 +449,28 @@ class Engine : public EngineBase {
   }
   static dim3 grid_xd(const TileX& g) { return dim3(g.nchunk * g.n_outer); }
   unsigned next_epoch() { return ++epoch; }
+  // rank gates folded into the slab x sweeps (comm.cuh): the x sweep announces itself on entry, waits for every peer,
+  // and its last CTA announces completion; the kernel that consumes what the peers wrote waits for that.
+  PeerGate gate_none() const { PeerGate g; g.comm.G = 1; return g; }
+  PeerGate gate_xsweep() {
+    PeerGate g;
+    g.comm = comm;
+    g.signal_in = g.wait_epoch = next_epoch();
+    g.signal_out = gate_pending = next_epoch();
+    g.ticket = ticket;
+    return g;
+  }
+  PeerGate gate_consumer() {
+    PeerGate g;
+    g.comm = comm;
+    g.wait_epoch = gate_pending;
+    gate_pending = 0;
+    return g;
+  }
+  // for consumers without a gate of their own
+  void gate_wait_kernel() {
+    if (G > 1 && gate_pending) L("k_gate_wait", k_gate_wait, dim3(1), dim3(32), 0, st, gate_consumer());
+  }
   void barrier() {
     if (G > 1) L("k_peer_barrier", k_peer_barrier, dim3(1), dim3(32), 0, st, comm, next_epoch());
   }
@@ -464,6 +494,24 @@ class Engine : public EngineBase {
   // programmatic dependent launch for the kernels that call pdl_wait() (single-GPU handles only: the
   // slab path orders its x sweeps with k_peer_barrier launches, which stay fully serialised).
   // Off while profiling: the bracketing events would serialise the launches anyway.
+#if !defined(GLIA_SIMT_EMU)
+  // GLIA_RD_TMA=1: the preconditioner's y sweeps through the TMA / mbarrier kernel (sweeps_tma.cuh) -- the A/B
+  // experiment of round 2; single-GPU handles only.  The tensor map covers shat, whose address never changes.
+  bool use_tma = false;
+  bool tmap_ready = false;
+  CUtensorMap tmap_shat;
+  bool tma_map() {
+    if (!tmap_ready) {
+      const long words = (long)n[2] * (long)sizeof(T) / 4;
+      const int box_words = (int)(sizeof(C) * SL / 4);
+      int rows = n[1] > 256 ? 256 : n[1];
+      if (!make_tile_map_y(&tmap_shat, (void*)shat, n0l, n[1], words, box_words, rows))
+        throw EngineError{"GLIA_RD_TMA=1: cuTensorMapEncodeTiled is unavailable or rejected the tile map"};
+      tmap_ready = true;
+    }
+    return true;
+  }
+#endif
   bool use_pdl = true;  // GLIA_RD_PDL=0 turns it off
   // slab handles: only the rank-local chains (z, y sweeps, scalar kernels, vector update) overlap; the
   // peer x sweeps and the k_peer_barrier launches around them go through L() and stay fully serialised,
@@ -560,20 +608,23 @@ class Engine : public EngineBase {
         const dim3 gr = grid_pipe<N>(ntiles);
         nblk = (int)gr.x;
         bool launched = false;
+        // slab handles: this sweep consumes what the peers' x sweeps wrote into acc (gate left pending by dapply_dist)
+        const PeerGate gate = (G > 1 && gate_pending) ? gate_consumer() : gate_none();
         if constexpr (EPI != EPI_ADD && EPI != EPI_SET) {
           if (acc_extra) {
             const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk};
             LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
                st, ntiles, rows_s(g, x), rows_s(g, kfield), a2, rows_s(g, out1), rows_s(g, out2),
-               (const C*)tw_for(nline, g), alpha, pp, done);
+               (const C*)tw_for(nline, g), alpha, pp, done, gate);
             launched = true;
           }
         }
         if (!launched)
           LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
              ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2),
-             (const C*)tw_for(nline, g), alpha, pp, done);
+             (const C*)tw_for(nline, g), alpha, pp, done, gate);
       } else {  // three tiles exceed shared memory (double precision at 512 points): one tile per CTA
+        gate_wait_kernel();
         if (acc_extra) throw EngineError{"internal: two-field accumulator needs the pipelined sweep"};
         if (keep_x && smem_s2<N>() > 227 * 1024)
           throw EngineError{"512-point lines in double precision: the operatorA sweep does not fit shared memory"};
@@ -603,7 +654,10 @@ class Engine : public EngineBase {
       sweep_deriv2_z<0>("kz_deriv2.side", x, kfield, done);
       z_side = false; z_out_override = nullptr; pdl_hold = false;
     }
-    barrier();
+    // Rank ordering around the x sweep: the pipelined kernel carries its own gates (entry: announce + wait for every
+    // peer; exit: the last CTA announces), and the y sweep below waits for the peers' exit announcements in its
+    // prologue -- no stand-alone barrier launches in the hot loop.  The serial order (profiling pass, GLIA_RD_XZ=0)
+    // hands acc to the z sweep, which has no gate: it keeps the trailing barrier kernel.
     GLIA_DISPATCH_N(n[0], {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = txd.nchunk * txd.n_outer;
@@ -613,15 +667,19 @@ class Engine : public EngineBase {
           const int cap = xz_ctas > 0 ? xz_ctas : (int)(0.75 * nsm * pipe_ctas<T, N>());
           if ((int)gx.x > cap) gx.x = (unsigned)(cap < 1 ? 1 : cap);
         }
+        PeerGate gate = gate_xsweep();
+        if (!overlapped) { gate.signal_out = 0; gate_pending = 0; }
         L("kx_deriv2_dist", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, gx,
           block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)const_cast<T*>(kpen), txd}, ra, ra, ra,
-          (const C*)tw[0], (T)0, (double*)nullptr, done);
+          (const C*)tw[0], (T)0, (double*)nullptr, done, gate);
+        if (!overlapped) barrier();
       } else {
+        barrier();
         L("kx_deriv2_dist", kx_deriv2_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, xr, (const C*)kpen, ar,
           (const C*)tw[0], done);
+        barrier();
       }
     });
-    barrier();
     if (overlapped) fork.end(st);
     else sweep_deriv2_z<1>("kz_deriv2.add", x, kfield, done);
     const char* ytag = EPI == EPI_MATVEC ? "ks_deriv2.y.matvec" : (EPI == EPI_RHS ? "ks_deriv2.y.rhs" : "ks_deriv2.y.epi");
@@ -653,8 +711,14 @@ class Engine : public EngineBase {
     GLIA_DISPATCH_N(n[1], {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
+#if !defined(GLIA_SIMT_EMU)
+        if (use_tma && tma_map()) {
+          LP("ks_c2c.y", ks_c2c_tma<T, N, -1>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, ty.nchunk,
+             tmap_shat, (const C*)tw[1], done);
+        } else
+#endif
         LP("ks_c2c.y", ks_c2c_pipe<T, N, -1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, gate_none());
       } else {
         LP("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
            (const C*)tw[1], done);
@@ -663,24 +727,24 @@ class Engine : public EngineBase {
     if (G > 1) {
       const TileX txd = tile_xd();
       const PeerRows<T> sr = rows((const T*)shat, 1), sw = rows((const T*)shat, 2);
-      barrier();
       GLIA_DISPATCH_N(n[0], {
-        if constexpr (pipe_fits<T, N>()) {
+        if constexpr (pipe_fits<T, N>()) {  // gated like the D-apply's x sweep; the inverse y sweep below is the consumer
           const int ntiles = txd.nchunk * txd.n_outer;
           L("kx_pc_dist", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], done);
+            RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], done, gate_xsweep());
         } else {
+          barrier();
           L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr, (const C*)tw[0], sym, n[1],
             done);
+          barrier();
         }
       });
-      barrier();
     } else {
       GLIA_DISPATCH_N(n[0], {
         if constexpr (pipe_fits<T, N>()) {
           const int ntiles = tx.nchunk * tx.n_outer;
           LP("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done);
+            rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done, gate_none());
         } else {
           L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat, (const C*)tw[0], sym, n[1], done);
         }
@@ -689,17 +753,28 @@ class Engine : public EngineBase {
     GLIA_DISPATCH_N(n[1], {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
+#if !defined(GLIA_SIMT_EMU)
+        if (use_tma && tma_map()) {
+          LP("ks_c2c.y", ks_c2c_tma<T, N, +1>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, ty.nchunk,
+             tmap_shat, (const C*)tw[1], done);
+        } else
+#endif
         LP("ks_c2c.y", ks_c2c_pipe<T, N, +1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done);
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, (G > 1 && gate_pending) ? gate_consumer() : gate_none());
       } else {
+        gate_wait_kernel();
         LP("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
            (const C*)tw[1], done);
       }
     });
     GLIA_DISPATCH_N(n[2], {
       nblk = (int)grid_z<N>().x;
-      LP(zout ? (want_rz ? "kz_c2r.rz" : "kz_c2r") : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), (const C*)shat,
-                   zout, want_rz ? (const T*)rin : (const T*)nullptr, pp, (const C*)tw[2], done);
+      if (zout && want_rz)
+        LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
+           lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done);
+      else
+        LP(zout ? "kz_c2r" : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(),
+           (const C*)shat, zout, (const T*)nullptr, pp, (const C*)tw[2], done);
     });
     return nblk;
   }
@@ -1123,7 +1198,7 @@ class Engine : public EngineBase {
         GLIA_DISPATCH_N(n[0], {
           if constexpr (pipe_fits<T, N>())
             L("probe", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-              RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], (const int*)nullptr);
+              RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], (const int*)nullptr, gate_none());
         });
       } else {
         const PeerRows<T> xr = rows(p, 1), ar = rows(acc, 2);
@@ -1132,7 +1207,7 @@ class Engine : public EngineBase {
           if constexpr (pipe_fits<T, N>())
             L("probe", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, grid_pipe<N>(ntiles),
               block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)kT, txd}, ra, ra, ra, (const C*)tw[0], (T)0,
-              (double*)nullptr, (const int*)nullptr);
+              (double*)nullptr, (const int*)nullptr, gate_none());
         });
       }
     }

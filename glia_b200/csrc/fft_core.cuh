@@ -71,6 +71,26 @@ __device__ __forceinline__ void pdl_wait() {
 #define GLIA_PDL_ENTRY_LATE(done) \
   if constexpr (!(GLIA_PDL_TOP)) { pdl_wait(); if ((done) && *(done)) return; }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no registers, no scoreboard stall --------------
+#if defined(GLIA_SIMT_EMU)
+__device__ inline void cp_async16(void* smem, const void* g) { std::memcpy(smem, g, 16); }
+__device__ inline void cp_async8(void* smem, const void* g) { std::memcpy(smem, g, 8); }
+__device__ inline void cp_async_commit() {}
+template <int K> __device__ inline void cp_async_wait() {}
+#else
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+#endif
+
 // software prefetch of one 128-byte line into L1 (for operands an epilogue reads long after the
 // kernel starts: zero registers held across the transform)
 template <typename V>
@@ -83,12 +103,23 @@ __device__ __forceinline__ void prefetch_l1(const V* p) {
 }
 
 // ---------------------------------------------------------------- plans ----
-template <int N> struct FftPlan;
-template <> struct FftPlan<32>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 4,  R2 = 1; };
-template <> struct FftPlan<64>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 8,  R2 = 1; };
-template <> struct FftPlan<128> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 8,  R2 = 1; };
-template <> struct FftPlan<256> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 16, R2 = 1; };
-template <> struct FftPlan<512> { static constexpr int E = 16, P = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+// FftPlan<N, V>: V = 0 the default plan; V = 1 the plan of the Z geometry (differs at 512 points only, below)
+template <int N, int V = 0> struct FftPlan;
+template <> struct FftPlan<32, 0>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 4,  R2 = 1; };
+template <> struct FftPlan<64, 0>  { static constexpr int E = 8,  P = 2, R0 = 8,  R1 = 8,  R2 = 1; };
+template <> struct FftPlan<128, 0> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 8,  R2 = 1; };
+template <> struct FftPlan<256, 0> { static constexpr int E = 16, P = 2, R0 = 16, R1 = 16, R2 = 1; };
+template <> struct FftPlan<512, 0> { static constexpr int E = 16, P = 3, R0 = 8,  R1 = 8,  R2 = 8; };
+template <int N> struct FftPlan<N, 1> : FftPlan<N, 0> {};
+// 512 points need three passes at 16 values per thread.  With radices 2 x 16 x 16 the line is, after the radix-2
+// first pass, two independent 256-point transforms, each owned by one half of the line's 32 threads (the second
+// exchange only needs that half to meet: LineFft::exchange with a half barrier), and a thread holds 23 instead of 28
+// inter-pass twiddles.  Measured on one B200 at 512^3 (profiles/r2h_plan512_ab.txt): the warp-synchronous Z sweeps
+// gain 9-11 % (kz_deriv2 512 -> 466 us, kz_c2r.rz 405 -> 361 us, kz_r2c 254 -> 234 us) -- fewer live registers,
+// no spill -- while the S sweeps LOSE 5-15 % (x.matvec 624 -> 714 us: the radix-16 butterflies spill more under the
+// 128-register cap of a 512-thread CTA than the half barriers give back).  So: Z geometry only.
+template <> struct FftPlan<512, 1> { static constexpr int E = 16, P = 3, R0 = 2,  R1 = 16, R2 = 16; };
+template <int N> __host__ __device__ constexpr int zplan() { return 1; }
 
 // cos(2 pi j / 32), j = 0..8 -- enough for every radix <= 32 by symmetry
 __host__ __device__ constexpr double cos32(int j) {
@@ -182,9 +213,9 @@ __device__ __forceinline__ void dft_reg(cplx<T>* v) {
 }
 
 // ------------------------------------------------------- the line FFT ----
-template <typename T, int N>
+template <typename T, int N, int V = 0>
 struct LineFft {
-  using PL = FftPlan<N>;
+  using PL = FftPlan<N, V>;
   static constexpr int E = PL::E, P = PL::P, TPL = N / E;
   __host__ __device__ static constexpr int R(int p) { return p == 0 ? PL::R0 : (p == 1 ? PL::R1 : PL::R2); }
   __host__ __device__ static constexpr int Np(int p) {
@@ -268,16 +299,21 @@ struct LineFft {
       }
     }
   }
+  // After a radix-2 first pass the two halves of the line never exchange data again: passes >= 1 touch only the
+  // half [h N/2, (h+1) N/2) with h = t / (TPL/2), in both placements.
+  static constexpr bool SPLIT = (P == 3 && PL::R0 == 2);
   // move registers from the pass-`pw` placement to the pass-`pr` placement
   template <int pw, int pr, class AM, class SY>
   __device__ static __forceinline__ void exchange(cplx<T> (&v)[E], cplx<T>* sm, AM am, SY sync, int t) {
-    sync();  // previous readers of sm are done
+    constexpr bool HALF = SPLIT && pw >= 1 && pr >= 1;
+    const int h = t / (TPL / 2);
+    if constexpr (HALF) sync.half(h); else sync();  // previous readers of sm are done
     GLIA_UNROLL
     for (int g = 0; g < Gp(pw); ++g) {
       GLIA_UNROLL
       for (int a = 0; a < R(pw); ++a) sm[am(loc<pw>(t, g, a))] = v[g * R(pw) + a];
     }
-    sync();
+    if constexpr (HALF) sync.half(h); else sync();
     GLIA_UNROLL
     for (int g = 0; g < Gp(pr); ++g) {
       GLIA_UNROLL

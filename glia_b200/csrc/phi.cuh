@@ -63,7 +63,7 @@ template <typename T, int N, int GAUSS>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_filter(LinesZ ln, const T* __restrict__ in, T* out, const T* __restrict__ symtab, const cplx<T>* __restrict__ twt,
           GaussPhi<T> gp, int n1) {
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);

@@ -23,8 +23,9 @@
 #include <unordered_map>
 
 #define GLIA_UNROLL _Pragma("unroll")
+// (128-byte aligned: bulk tensor copies -- sweeps_tma.cuh -- need their shared-memory tiles on 128-byte boundaries)
 #define GLIA_DYN_SMEM(name) \
-  extern __shared__ __align__(16) unsigned char _glia_dyn_smem[]; \
+  extern __shared__ __align__(128) unsigned char _glia_dyn_smem[]; \
   unsigned char* name = _glia_dyn_smem
 
 namespace simt {

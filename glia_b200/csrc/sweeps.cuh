@@ -63,8 +63,22 @@ __device__ __forceinline__ void block_reduce_store(double (&val)[NV], double* __
   __syncthreads();
 }
 
-struct SyncCta { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
-struct SyncWarp { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+// CTA-wide barrier of the S geometry; half(h): the named barrier of thread half h (threads [h B/2, (h+1) B/2) of a
+// B-thread CTA -- with threadIdx = t * SL + l these are the threads of line half h, see LineFft::SPLIT)
+struct SyncCta {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+  __device__ __forceinline__ void half(int h) const {
+#if defined(GLIA_SIMT_EMU)
+    emu_half_barrier(h);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(h + 1), "r"((int)blockDim.x / 2) : "memory");
+#endif
+  }
+};
+struct SyncWarp {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+  __device__ __forceinline__ void half(int) const { __syncwarp(); }
+};
 
 template <int TPL> struct ZSync { using type = SyncWarp; };
 template <> struct ZSync<64> { using type = SyncCta; };
@@ -83,10 +97,10 @@ template <int N> __host__ __device__ constexpr int zlines() { return 256 / (N / 
 template <int N> __host__ __device__ constexpr int zthreads() { return zlines<N>() * (N / FftPlan<N>::E); }
 
 // v <- D_axis(v): forward, i*w/N, inverse
-template <typename T, int N, class AM, class SY>
-__device__ __forceinline__ void deriv_inplace(cplx<T> (&v)[FftPlan<N>::E], const typename LineFft<T, N>::Tw& tw,
+template <typename T, int N, int V = 0, class AM, class SY>
+__device__ __forceinline__ void deriv_inplace(cplx<T> (&v)[FftPlan<N>::E], const typename LineFft<T, N, V>::Tw& tw,
                                               cplx<T>* sm, AM am, SY sy, int t) {
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, V>;
   F::forward(v, tw, sm, am, sy, t);
   F::mult_iw(v, t);
   F::inverse(v, tw, sm, am, sy, t);
@@ -367,7 +381,7 @@ ks_pc(TileS geo, cplx<T>* shat, const cplx<T>* __restrict__ twt, PcSym<T> sym, i
 // common Z-geometry prologue
 template <typename T, int N>
 struct ZCtx {
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   static constexpr int TPL = F::TPL, LPC = zlines<N>();
   int t, lp;
   long pair;
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(zthreads<N>(), MINB)
 kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, const cplx<T>* __restrict__ twt,
           const int* __restrict__ done) {
   GLIA_PDL_ENTRY_EARLY(done);
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
@@ -408,7 +422,7 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
       v[g * F::R(0) + a] = {ld_stream(x + la + pos), ld_stream(x + lb + pos)};
       kk[g * F::R(0) + a] = {ld_stream(kf + la + pos), ld_stream(kf + lb + pos)};
     }
-  deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
+  deriv_inplace<T, N, zplan<N>()>(v, tw, sm, z.am(), sy, z.t);
   GLIA_UNROLL
   for (int e = 0; e < E; ++e) { v[e].x *= kk[e].x; v[e].y *= kk[e].y; }
   if (ADD) {  // the accumulator is fetched now so that its latency hides behind the second derivative
@@ -418,7 +432,7 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
       kk[e] = {acc[la + pos], acc[lb + pos]};
     }
   }
-  deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
+  deriv_inplace<T, N, zplan<N>()>(v, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
     for (int g = 0; g < F::Gp(0); ++g)
@@ -437,7 +451,7 @@ kz_deriv2(LinesZ ln, const T* __restrict__ x, const T* __restrict__ kf, T* acc, 
 template <typename T, int N, int ADD>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_deriv1(LinesZ ln, const T* __restrict__ in, T* out, const cplx<T>* __restrict__ twt) {
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
@@ -462,7 +476,7 @@ kz_deriv1(LinesZ ln, const T* __restrict__ in, T* out, const cplx<T>* __restrict
       o[e] = {out[la + pos], out[lb + pos]};
     }
   }
-  deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
+  deriv_inplace<T, N, zplan<N>()>(v, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
     for (int e = 0; e < E; ++e) {
@@ -481,7 +495,7 @@ template <typename T, int N>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_gradprod(LinesZ ln, const T* __restrict__ c, const T* __restrict__ p, T* Tk, T* Tr, T coef,
             const cplx<T>* __restrict__ twt) {
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
@@ -516,8 +530,8 @@ kz_gradprod(LinesZ ln, const T* __restrict__ c, const T* __restrict__ p, T* Tk, 
       Tr[lb + pos] = o[e].y + coef * wb;
     }
   }
-  deriv_inplace<T, N>(v, tw, sm, z.am(), sy, z.t);
-  deriv_inplace<T, N>(u, tw, sm, z.am(), sy, z.t);
+  deriv_inplace<T, N, zplan<N>()>(v, tw, sm, z.am(), sy, z.t);
+  deriv_inplace<T, N, zplan<N>()>(u, tw, sm, z.am(), sy, z.t);
   if (z.active) {
     GLIA_UNROLL
     for (int e = 0; e < E; ++e) {
@@ -542,7 +556,7 @@ __global__ void __launch_bounds__(zthreads<N>())
 kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal_a, cplx<T>* shat,
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   GLIA_PDL_ENTRY_EARLY(done);
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
@@ -603,12 +617,17 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
 // Z-geometry complex-to-real of the packed half spectrum, with the PCG epilogue:
 // partial sums {<z,z>, <r,z>} (VecNorm(Z), VecXDot(Z,R) of KSPSolve_CG).
 //   zout may be null (only the norm is wanted, e.g. rnorm0 = ||M^-1 b||).
+//   EPI 0: no sums; 1: <z,z> (and <r,z> with plain loads if r); 2: <z,z>, <r,z> with the two r lines of a pair
+//   staged through shared memory by cp.async while the inverse transform runs (the epilogue's r loads were this
+//   kernel's top stall: 56 % long-scoreboard, profiles/r1c_ncu_source_summary.txt)
+template <int N, typename T>
+__host__ __device__ constexpr size_t smem_z_rstage() { return (size_t)zlines<N>() * 2 * N * sizeof(T); }
 template <typename T, int N, int EPI>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict__ r, double* partial,
        const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   GLIA_PDL_ENTRY_EARLY(done);
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
   GLIA_DYN_SMEM(smraw);
   cplx<T>* sm = reinterpret_cast<cplx<T>*>(smraw);
@@ -620,9 +639,13 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
   const long la = z.pair * 2 * N, lb = la + N;
   const long oa = z.pair * 2 * (N / 2), ob = oa + N / 2;
   AmZ am = z.am();
-  if (EPI && r) {
-    // the <r,z> epilogue reads r only after the whole inverse transform: start the two lines (2N
-    // contiguous values) towards L1 now (ncu: 49 % of this kernel's stall samples sat on those loads)
+  [[maybe_unused]] T* rst = nullptr;
+  if constexpr (EPI == 2) {
+    rst = reinterpret_cast<T*>(smraw + sizeof(cplx<T>) * zlines<N>() * zpad<N>()) + (size_t)z.lp * 2 * N;
+    constexpr int PER = 16 / (int)sizeof(T), CH = 2 * N / PER;
+    for (int i = z.t; i < CH; i += F::TPL) cp_async16(rst + i * PER, r + la + i * PER);
+    cp_async_commit();
+  } else if (EPI && r) {
     constexpr int PER = 128 / (int)sizeof(T);
     for (int i = z.t; i < 2 * N / PER; i += F::TPL) prefetch_l1(r + la + i * PER);
   }
@@ -646,6 +669,10 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
     GLIA_UNROLL
     for (int cc = 0; cc < F::RL; ++cc) v[g * F::RL + cc] = sm[am(F::template loc<F::P - 1>(z.t, g, cc))];
   F::inverse(v, tw, sm, am, sy, z.t);
+  if constexpr (EPI == 2) {
+    cp_async_wait<0>();
+    sy();  // the r pieces fetched by the other threads of this line pair
+  }
   double acc[2] = {0.0, 0.0};
   GLIA_UNROLL
   for (int g = 0; g < F::Gp(0); ++g)
@@ -657,7 +684,8 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
         if (zout) { zout[la + pos] = zv.x; zout[lb + pos] = zv.y; }
         if (EPI) {
           acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
-          if (r) acc[1] += (double)ld_stream(r + la + pos) * (double)zv.x + (double)ld_stream(r + lb + pos) * (double)zv.y;
+          if constexpr (EPI == 2) acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
+          else if (r) acc[1] += (double)ld_stream(r + la + pos) * (double)zv.x + (double)ld_stream(r + lb + pos) * (double)zv.y;
         }
       }
     }

@@ -3,9 +3,9 @@
 //
 // kz_deriv2 puts the 64 scalar loads of a line pair's x and k in flight at once; at 512-point lines
 // that costs 168 registers = ONE 256-thread CTA per SM.  Here the x lines of the NEXT line-pair group
-// ride into shared memory on cp.async while the current group is transformed, k is sent towards L1 on
-// entry of the round and read at the point of use, and nothing but the 16 complex values of the
-// transform lives across it.  A line pair belongs to N/E <= 32 threads of one warp, which fetch exactly
+// ride into shared memory on cp.async while the current group is transformed, k (and the accumulator)
+// follow through the same stage during the transforms, and nothing but the 16 complex values of the
+// transform lives in registers across it.  A line pair belongs to N/E <= 32 threads of one warp, which fetch exactly
 // the bytes they later read, so the whole pipeline needs __syncwarp only: no CTA barrier, warps drift.
 // Measured on the B200 (profiles/r2d_zpipe_twldg_ab.txt): 49.7 -> 45.8 us at 256^3, 603 -> 526 us at
 // 512^3 (f32).
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(zthreads<N>(), zpipe_ctas<T, N>())
 kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restrict__ kf, T* acc,
                const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
   GLIA_PDL_ENTRY_EARLY(done);
-  using F = LineFft<T, N>;
+  using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E, TPL = F::TPL, LPC = zlines<N>();
   static_assert(TPL <= 32, "a line pair must live inside one warp");
   GLIA_DYN_SMEM(smraw);
@@ -59,8 +59,8 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
     long p = (long)group * LPC + lp;
     return p < ln.npairs ? p : ln.npairs - 1;  // ragged tail: re-do the last pair, stores predicated
   };
-  auto prefetch = [&](T* stage, int group) {
-    const char* src = reinterpret_cast<const char*>(x + pair_of(group) * 2 * N);
+  auto prefetch = [&](T* stage, const T* field, int group) {
+    const char* src = reinterpret_cast<const char*>(field + pair_of(group) * 2 * N);
     GLIA_UNROLL
     for (int i = 0; i < CH / TPL; ++i) {
       const int c = t + i * TPL;
@@ -69,23 +69,16 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
   };
 
   int group = blockIdx.x, s = 0;
-  if (group < ngroups) prefetch(stage0, group);
+  if (group < ngroups) prefetch(stage0, x, group);
   cp_async_commit();
   for (; group < ngroups; group += gridDim.x, s ^= 1) {
     T* st = stage0 + (size_t)s * (2 * N);
     const int next = group + gridDim.x;
-    if (next < ngroups) prefetch(stage0 + (size_t)(s ^ 1) * (2 * N), next);
+    if (next < ngroups) prefetch(stage0 + (size_t)(s ^ 1) * (2 * N), x, next);
     cp_async_commit();
     const long pair = pair_of(group);
     const bool active = (long)group * LPC + lp < ln.npairs;
     const long la = pair * 2 * N, lb = la + N;
-    {  // k (and the accumulator of the ADD form) towards L1: read after the first / second derivative
-      constexpr int PER = 128 / (int)sizeof(T);
-      for (int i = t; i < 2 * N / PER; i += TPL) {
-        prefetch_l1(kf + la + i * PER);
-        if (ADD) prefetch_l1(acc + la + i * PER);
-      }
-    }
     cp_async_wait<1>();
     sy();  // the copies of the other lanes of this pair are visible too
     cplx<T> v[E];
@@ -94,26 +87,40 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
       const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
       v[e] = {st[pos], st[N + pos]};
     }
-    deriv_inplace<T, N>(v, tw, sm, am, sy, t);
+    // the stage of this round now carries, in turn, k (in flight during the first derivative) and -- ADD form --
+    // the accumulator (in flight during the second): nothing but the transform's 16 complex values lives in
+    // registers across it (same scheme as the S sweeps, sweeps_pipe.cuh)
+    sy();
+    prefetch(st, kf, group);
+    cp_async_commit();
+    deriv_inplace<T, N, zplan<N>()>(v, tw, sm, am, sy, t);
+    cp_async_wait<0>();
+    sy();
     GLIA_UNROLL
     for (int e = 0; e < E; ++e) {
       const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
-      v[e].x *= kf[la + pos];
-      v[e].y *= kf[lb + pos];
+      v[e].x *= st[pos];
+      v[e].y *= st[N + pos];
     }
-    deriv_inplace<T, N>(v, tw, sm, am, sy, t);
+    if (ADD) {
+      sy();
+      prefetch(st, (const T*)acc, group);
+    }
+    cp_async_commit();
+    deriv_inplace<T, N, zplan<N>()>(v, tw, sm, am, sy, t);
+    cp_async_wait<0>();
+    sy();
     if (active) {
       GLIA_UNROLL
       for (int e = 0; e < E; ++e) {
         const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
         cplx<T> o = v[e];
-        if (ADD) { o.x += acc[la + pos]; o.y += acc[lb + pos]; }
+        if (ADD) { o.x += st[pos]; o.y += st[N + pos]; }
         acc[la + pos] = o.x;
         acc[lb + pos] = o.y;
       }
     }
-    // this round's reads of stage s precede the transforms' __syncwarp()s, so the prefetch the next
-    // round issues into it cannot overtake them
+    sy();  // the next round refills this stage two rounds later; its other stage is refilled at the top
   }
   cp_async_wait<0>();
 }

@@ -40,6 +40,7 @@ struct Ctx {
   dim3 tid, bid, bdim, gdim;
   unsigned char* smem = nullptr;
   std::barrier<>* cta_bar = nullptr;
+  std::barrier<>* half_bar[2] = {nullptr, nullptr};  // bar.sync 1 / 2 over the lower / upper half of the CTA's threads
   std::barrier<>* warp_bar = nullptr;
   unsigned char* warp_slots = nullptr;  // 32 x 16 bytes scratch for shuffles
   int lane = 0;
@@ -52,6 +53,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
   const int nwarp = (nthr + 31) / 32;
   std::vector<unsigned char> smem(smem_bytes + 64);
   std::barrier<> cta_bar(nthr);
+  std::barrier<> half_lo(nthr / 2 > 0 ? nthr / 2 : 1), half_hi(nthr - nthr / 2 > 0 ? nthr - nthr / 2 : 1);
   std::vector<std::unique_ptr<std::barrier<>>> wbars;
   std::vector<std::vector<unsigned char>> wslots(nwarp, std::vector<unsigned char>(32 * 16));
   for (int w = 0; w < nwarp; ++w) {
@@ -68,6 +70,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
       c.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
       c.smem = smem.data();
       c.cta_bar = &cta_bar;
+      c.half_bar[0] = &half_lo;
+      c.half_bar[1] = &half_hi;
       c.warp_bar = wbars[i / 32].get();
       c.warp_slots = wslots[i / 32].data();
       c.lane = i % 32;
@@ -90,6 +94,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
 #define gridDim (emu::ctx.gdim)
 
 inline void __syncthreads() { emu::ctx.cta_bar->arrive_and_wait(); }
+inline void emu_half_barrier(int h) { emu::ctx.half_bar[h]->arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.warp_bar->arrive_and_wait(); }
 
 template <class T>
