@@ -71,7 +71,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-3 gradient / Hessian / Phi timings")
     ap.add_argument("--members", type=int, default=64, help="ensemble workload: number of members (<= 64)")
-    ap.add_argument("--concurrency", type=int, default=4, help="ensemble workload: members in flight per GPU")
+    ap.add_argument("--concurrency", type=int, default=1,
+                    help="ensemble workload: ensemble handles (host threads) per GPU; a rank's members are split over them")
     ap.add_argument("--no-base", action="store_true", help="slab workload: skip the 1-GPU run of the same grid")
     ap.add_argument("--ref-nt", type=int, default=None,
                     help="time steps per CPU sample (default: 3 for --impl reference, 1 for the in-line cpu_baseline)")
@@ -792,9 +793,11 @@ def run_slab(a):
 def run_ensemble(a):
     """Config 5 of BASELINE.json: 64 independent 128^3 forward solves, (kappa, rho) on an 8 x 8 grid
     (kappa in [0.005, 0.05] log-spaced, rho in [4, 15]), spread over the ranks (8 per GPU at
-    N = 8), `--concurrency` members in flight per GPU -- one handle (= one stream) each, driven from
-    host threads (ctypes releases the GIL inside the library).  Replicas only: no collective on the
-    data path; the value is aggregate member-time-steps per second."""
+    N = 8).  A rank's members ride in ONE ensemble handle (glia_rd_create_batch): the kernels carry a
+    member index, every member keeps its own coefficients, PCG state and iteration count, one set of
+    launches advances all of them.  `--concurrency` > 1 splits a rank's members over that many handles
+    driven from host threads (the round-1 arrangement, kept for comparison).  Replicas only: no collective
+    on the data path; the value is aggregate member-time-steps per second."""
     import threading
     import torch
     from glia_b200.rd import RDHandle
@@ -832,8 +835,10 @@ def run_ensemble(a):
     members = [(float(k), float(r)) for k in kappas for r in rhos][: a.members]
     mine = members[rank::world]
     conc = max(1, min(a.concurrency, len(mine)))
-    handles = [RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt) for _ in range(conc)]
-    outs = [torch.empty_like(c0d) for _ in range(conc)]
+    groups = [mine[j::conc] for j in range(conc)]          # one ensemble handle per group
+    handles = [RDHandle(a.n, a.precision, device=local, dt_ctx=a.dt, nbatch=len(g)) for g in groups]
+    c0b = [c0d.unsqueeze(0).repeat(len(g), 1, 1, 1).contiguous() for g in groups]
+    outs = [torch.empty_like(x) for x in c0b]
     for h in handles:
         h.resize_history(a.nt, a.dt)
     torch.cuda.synchronize()
@@ -842,20 +847,21 @@ def run_ensemble(a):
 
     def worker(j, timed):
         torch.cuda.set_device(local)
-        h = handles[j]
-        its = 0
+        h, g = handles[j], groups[j]
         if timed:
             h.timer_start()
-        for kappa, rho in mine[j::conc]:
-            h.set_diffusion_tissue(wm, gm, csf, kappa, 0.0, 0.0, fsum)
-            h.set_reaction_tissue(wm, gm, csf, rho, 0.0, 0.0)
-            h.prec_factor()
-            its += h.solve_state(c0d, outs[j], 0)
+        # coefficient set-up is part of a member's cost (it differs per member), as in round 1
+        h.set_coefficients_batch(wm, gm, csf, [m[0] for m in g], 0.0, 0.0, fsum, [m[1] for m in g], 0.0, 0.0)
+        h.prec_factor()
+        its = h.solve_state(c0b[j], outs[j], 0)
         if timed:
             ms_thread[j] = h.timer_stop_ms()
         its_total[j] = its
 
     def sweep(timed):
+        if conc == 1:
+            worker(0, timed)
+            return
         th = [threading.Thread(target=worker, args=(j, timed)) for j in range(conc)]
         [t.start() for t in th]
         [t.join() for t in th]
@@ -879,25 +885,31 @@ def run_ensemble(a):
     F = float(np.dtype(dtype).itemsize) * a.n ** 3
     peak, peak_src = peaks()
     model_bytes = step_bytes_model(F, sum(its_total), nsolves, a.nt * len(mine)) - 7.0 * F * a.nt * len(mine)
+    per_member_its = [h.batch_iterations(True) for h in handles]
     line = {
         "metric": "rd_ensemble_member_time_steps_per_sec", "value": value, "unit": "member-time-steps/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
         "config": {"workload": f"config 5: {len(members)} independent {a.n}^3 RD forward solves, (kappa, rho) on an "
                                "8 x 8 grid, replicas only (no data-path collective)", "n": a.n, "nt": a.nt,
-                   "dt": a.dt, "members": len(members), "members_per_gpu": len(mine), "concurrency_per_gpu": conc,
-                   "l2": "a 128^3 field is 8 MB: the working set of a member lives in the 126 MB L2 by design; "
-                         "consecutive members use different coefficients, nothing is reused across timed steps "
-                         "except the tissue maps"},
+                   "dt": a.dt, "members": len(members), "members_per_gpu": len(mine),
+                   "ensemble_handles_per_gpu": conc, "members_per_handle": [len(g) for g in groups],
+                   "batching": "members ride in the kernels' member index (glia_rd_create_batch): one set of launches "
+                               "per PCG iteration for all members of a handle",
+                   "value_per_gpu": value / world,
+                   "l2": "a 128^3 field is 8 MB; a handle's members together exceed the 126 MB L2 from 3 members on "
+                         "(k, rho, 5 PCG vectors, histories per member)"},
         "pcg_iterations": {"state": int(sum(its_total)), "solves": nsolves,
-                           "mean_per_solve": sum(its_total) / max(nsolves, 1)},
+                           "mean_per_solve": sum(its_total) / max(nsolves, 1),
+                           "per_member_min_max": [int(min(min(x) for x in per_member_its)),
+                                                  int(max(max(x) for x in per_member_its))]},
         "gpu_launches": int(launches) * world, "clocks": clocks,
         "roofline": {"bound": "hbm", "whole_step": {"alg_bytes_per_gpu": model_bytes,
                                                      "achieved": model_bytes * a.steps / (ms * 1e-3) / 1e9,
                                                      "frac": model_bytes * a.steps / (ms * 1e-3) / 1e9 / peak},
                      "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                     "note": "forward only: A_min model F*[sum_solves(33+30 m_i) + 3 nt] per member; at 128^3 the "
-                             "path is launch- and latency-bound, not HBM-bound"},
+                     "note": "forward only: A_min model F*[sum_solves(33+30 m_i) + 3 nt] per member, with every "
+                             "member's own iteration counts"},
     }
     if rank == 0:
         print(json.dumps(line), flush=True)

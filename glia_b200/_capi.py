@@ -23,6 +23,10 @@ SIGNATURES = {
     "glia_rd_build_info": (C.c_char_p, []),
     "glia_rd_create": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D]),
     "glia_rd_create_slab": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D, _I, _I]),
+    "glia_rd_create_batch": (_I, [C.POINTER(_P), C.POINTER(_I), _I, _I, _D, _I]),
+    "glia_rd_batch_size": (_I, [_P, C.POINTER(_I)]),
+    "glia_rd_batch_iterations": (_I, [_P, C.POINTER(_I), _I]),
+    "glia_rd_set_coefficients_batch": (_I, [_P, _P, _P, _P, C.POINTER(_D), _D, _D, _D, C.POINTER(_D), _D, _D]),
     "glia_rd_ipc_export": (_I, [_P, _I, _P]),
     "glia_rd_ipc_connect": (_I, [_P, _I, _P]),
     "glia_rd_ipc_disconnect": (_I, [_P, _I]),

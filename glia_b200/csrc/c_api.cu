@@ -45,8 +45,8 @@ const char* glia_rd_build_info(void) {
 #endif
 }
 
-int glia_rd_create_slab(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx, int rank,
-                        int nranks) {
+static int create_any(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx, int rank, int nranks,
+                      int nbatch) {
   if (!out) return 2;
   *out = nullptr;
   glia_rd_t* h = new glia_rd();
@@ -61,8 +61,8 @@ int glia_rd_create_slab(glia_rd_t** out, const int n[3], int precision, int devi
     if (device < 0 || device >= ndev) throw EngineError{"device ordinal out of range"};
 #endif
     if (!n) throw EngineError{"n is null"};
-    if (precision == GLIA_RD_F32) h->eng = make_engine_f32(n, device, dt_ctx, rank, nranks);
-    else if (precision == GLIA_RD_F64) h->eng = make_engine_f64(n, device, dt_ctx, rank, nranks);
+    if (precision == GLIA_RD_F32) h->eng = make_engine_f32(n, device, dt_ctx, rank, nranks, nbatch);
+    else if (precision == GLIA_RD_F64) h->eng = make_engine_f64(n, device, dt_ctx, rank, nranks, nbatch);
     else throw EngineError{"precision must be 4 or 8"};
   } catch (const EngineError& e) {
     h->err = e.msg;
@@ -73,8 +73,35 @@ int glia_rd_create_slab(glia_rd_t** out, const int n[3], int precision, int devi
   }
   return 0;
 }
+int glia_rd_create_slab(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx, int rank,
+                        int nranks) {
+  return create_any(out, n, precision, device, dt_ctx, rank, nranks, 1);
+}
 int glia_rd_create(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx) {
-  return glia_rd_create_slab(out, n, precision, device, dt_ctx, 0, 1);
+  return create_any(out, n, precision, device, dt_ctx, 0, 1, 1);
+}
+int glia_rd_create_batch(glia_rd_t** out, const int n[3], int precision, int device, double dt_ctx, int nbatch) {
+  return create_any(out, n, precision, device, dt_ctx, 0, 1, nbatch);
+}
+int glia_rd_batch_size(glia_rd_t* h, int* nbatch) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!nbatch) throw EngineError{"null output pointer"};
+    *nbatch = E.v_nbatch();
+  });
+}
+int glia_rd_batch_iterations(glia_rd_t* h, int* its_per_member, int accumulated) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!its_per_member) throw EngineError{"null output pointer"};
+    E.v_batch_iterations(its_per_member, accumulated);
+  });
+}
+int glia_rd_set_coefficients_batch(glia_rd_t* h, const void* wm, const void* gm, const void* csf, const double* k_scale,
+                                   double k_gm_wm, double k_glm_wm, double filter_sum, const double* rho_scale,
+                                   double r_gm_wm, double r_glm_wm) {
+  return guarded(h, [&](EngineBase& E) {
+    if (!wm || !gm || !csf || !k_scale || !rho_scale) throw EngineError{"set_coefficients_batch: null argument"};
+    E.v_set_coefficients_batch(wm, gm, csf, k_scale, k_gm_wm, k_glm_wm, filter_sum, rho_scale, r_gm_wm, r_glm_wm);
+  });
 }
 int glia_rd_ipc_export(glia_rd_t* h, int which, void* handle64) {
   return guarded(h, [&](EngineBase& E) {

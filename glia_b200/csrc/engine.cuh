@@ -188,7 +188,9 @@ class Engine : public EngineBase {
   // [rank*n0l, (rank+1)*n0l) and sweeps the x lines with y in [rank*n1l, (rank+1)*n1l)
   int G = 1, rank = 0, n0l, n1l;
   int device = 0;     // CUDA ordinal this handle lives on; every entry point makes it current (make_current)
-  long nreal, ncplx;  // LOCAL element counts
+  long nreal, ncplx;  // LOCAL element counts of the whole handle (all ensemble members)
+  int nb = 1;         // ensemble members carried by this handle, fields laid out [nb][n0][n1][n2] (fft_core.cuh)
+  long nreal_m;       // elements of one member
   int n2c;            // n2/2: complex columns of the pair view
   cudaStream_t st = 0;
   rt::Timer timer;
@@ -229,7 +231,11 @@ class Engine : public EngineBase {
   T kavg[3] = {0, 0, 0};
   T k_scale = (T)1e-2;
   T dt_ctx;
-  PcSym<T> sym;
+  PcSym<T> sym;                  // member 0 (the only one unless this is an ensemble handle)
+  std::vector<T> kavg_m;         // ensemble: k-bar of every member (3 each); used when kavg_per_member
+  bool kavg_per_member = false;
+  PcSym<T>* syms_d = nullptr;    // device copy of every member's frozen symbol
+  std::vector<int> its_m, its_acc;  // per-member iteration counts: last solve / accumulated by the time loops
   // KSP settings (DiffusionSolver.cpp:27)
   double rtol = 1e-6, abstol = 1e-50, dtol = 1e4;
   int maxit = 5000;
@@ -268,7 +274,7 @@ class Engine : public EngineBase {
 
   int precision() const override { return (int)sizeof(T); }
 
-  Engine(const int nn[3], int device_, double dt_ctx_, int rank_ = 0, int nranks_ = 1) {
+  Engine(const int nn[3], int device_, double dt_ctx_, int rank_ = 0, int nranks_ = 1, int nbatch_ = 1) {
     for (int i = 0; i < 3; ++i) {
       n[i] = nn[i];
       if (!(n[i] == 32 || n[i] == 64 || n[i] == 128 || n[i] == 256 || n[i] == 512))
@@ -296,7 +302,11 @@ class Engine : public EngineBase {
     if (G == 1 || (sizeof(T) == 8 && (n[0] > 256 || n[1] > 256))) use_xz = false;
     if (use_xz) GLIA_CHECK(fork.create());
     timer.create();
-    nreal = (long)n0l * n[1] * n[2];
+    nb = nbatch_;
+    if (nb < 1 || nb > 4096) throw EngineError{"ensemble size must be in [1, 4096]"};
+    if (nb > 1 && G > 1) throw EngineError{"an ensemble handle cannot be slab-decomposed (members are independent: spread them over the GPUs)"};
+    nreal_m = (long)n0l * n[1] * n[2];
+    nreal = nreal_m * nb;
     ncplx = nreal / 2;
     n2c = n[2] / 2;
     dt_ctx = (T)dt_ctx_;
@@ -330,22 +340,27 @@ class Engine : public EngineBase {
     // partial-sum regions: enough for the largest grid of any reducing kernel
     npart = 4 * (nreal / 256 + 1024);
     GLIA_CHECK(rt::dev_malloc((void**)&partial, sizeof(double) * npart * 3));
-    GLIA_CHECK(rt::dev_malloc((void**)&scal, sizeof(double) * S_NSCAL));
-    GLIA_CHECK(rt::dev_malloc((void**)&iscal, sizeof(int) * I_NISCAL));
+    GLIA_CHECK(rt::dev_malloc((void**)&scal, sizeof(double) * S_NSCAL * nb));
+    GLIA_CHECK(rt::dev_malloc((void**)&iscal, sizeof(int) * I_NISCAL * nb));
+    GLIA_CHECK(rt::dev_malloc((void**)&syms_d, sizeof(PcSym<T>) * nb));
     GLIA_CHECK(rt::dev_malloc((void**)&ticket, sizeof(unsigned) * 4));
     GLIA_CHECK(rt::zero(ticket, sizeof(unsigned) * 4, st));
-    GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL, st));
-    GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL, st));
+    GLIA_CHECK(rt::zero(scal, sizeof(double) * S_NSCAL * nb, st));
+    GLIA_CHECK(rt::zero(iscal, sizeof(int) * I_NISCAL * nb, st));
     comm.err = iscal + I_COMM_ERR;
     comm.done = iscal + I_DONE;
     if (const char* e = std::getenv("GLIA_RD_PEER_TIMEOUT_S")) {
       const double sec = std::atof(e);
       if (sec > 0) comm.timeout_ns = (unsigned long long)(sec * 1e9);
     }
-    GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * (I_NISCAL + 1)));
-    h_iscal[I_NISCAL] = 0;
+    GLIA_CHECK(rt::host_malloc((void**)&h_iscal, sizeof(int) * (I_NISCAL * nb + 1)));
+    h_iscal[I_NISCAL * nb] = 0;
+    kavg_m.assign(3 * (size_t)nb, (T)0);
+    its_m.assign(nb, 0);
+    its_acc.assign(nb, 0);
     GLIA_CHECK(rt::host_malloc((void**)&h_out, sizeof(double) * 16));
     sym = PcSym<T>{dt_ctx, (T)0, (T)0, (T)0, (T)(1.0 / ((double)n[0] * n[1] * n[2]))};
+    upload_syms();
     GLIA_CHECK(rt::sync(st));
   }
   ~Engine() override {
@@ -359,7 +374,7 @@ class Engine : public EngineBase {
     if (G > 1) { rt::ipc_free(arena, arena_bytes, arena_handle); rt::ipc_free(hist_arena, hist_bytes, hist_handle); }
     else { rt::dev_free(arena); rt::dev_free(hist_arena); }
     for (int a = 0; a < 3; ++a) rt::dev_free(tw[a]);
-    rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal); rt::dev_free(ticket);
+    rt::dev_free(partial); rt::dev_free(scal); rt::dev_free(iscal); rt::dev_free(ticket); rt::dev_free(syms_d);
     rt::host_free(h_iscal); rt::host_free(h_out);
     rt::host_free(hs_in); rt::host_free(hs_out);
     for (int a = 0; a < 3; ++a) rt::dev_free(symtab[a]);
@@ -535,11 +550,11 @@ class Engine : public EngineBase {
   // that synchronises without solving (set_diffusion, gradient, ...) cannot return success after a rank
   // barrier timed out; the flag is cleared so that the handle stays usable once the peers are back.
   void sync() {
-    if (G > 1) GLIA_CHECK(rt::d2h(h_iscal + I_NISCAL, iscal + I_COMM_ERR, sizeof(int), st));
+    if (G > 1) GLIA_CHECK(rt::d2h(h_iscal + I_NISCAL * nb, iscal + I_COMM_ERR, sizeof(int), st));
     GLIA_CHECK(rt::sync(st));
     check_launch();
-    if (G > 1 && h_iscal[I_NISCAL]) {
-      h_iscal[I_NISCAL] = 0;
+    if (G > 1 && h_iscal[I_NISCAL * nb]) {
+      h_iscal[I_NISCAL * nb] = 0;
       rt::zero(iscal + I_COMM_ERR, sizeof(int), st);
       rt::sync(st);
       throw EngineError{"slab peer did not arrive at a rank barrier (timed out after GLIA_RD_PEER_TIMEOUT_S)"};
@@ -550,15 +565,21 @@ class Engine : public EngineBase {
   // ------------------------------------------------------------ geometry ----
   TileS tile_y() const { return TileS{(long)n2c, (long)n[1] * n2c, n2c / SL, n0l, 0}; }
   TileS tile_x() const { return TileS{(long)n[1] * n2c, (long)n2c, n2c / SL, n[1], 0}; }
-  LinesZ lines_z() const { return LinesZ{(long)n0l * n[1] / 2}; }
+  LinesZ lines_z() const { return LinesZ{(long)nb * n0l * n[1] / 2}; }          // every member's line pairs
+  LinesZ lines_z_member() const { return LinesZ{(long)n0l * n[1] / 2}; }
   template <int N> static size_t smem_s() { return sizeof(C) * N * SL; }
   template <int N> static size_t smem_s2() { return 2 * sizeof(C) * N * SL; }  // + the kept x tile
   template <int N> static size_t smem_z() { return sizeof(C) * zlines<N>() * zpad<N>(); }
   template <int N> static dim3 block_s() { return dim3(SL * (N / FftPlan<N>::E)); }
   static dim3 grid_s(const TileS& g) { return dim3(g.nchunk * g.n_outer); }
+  // Z kernels, one group of line pairs per CTA: CTAs per member (bpm) x members; a CTA never straddles two members
+  template <int N> int bpm_z() const {
+    const long np = lines_z_member().npairs;
+    return (int)((np + zlines<N>() - 1) / zlines<N>());
+  }
   template <int N> dim3 grid_z() const {
-    const long np = lines_z().npairs;
-    return dim3((unsigned)((np + zlines<N>() - 1) / zlines<N>()));
+    if (nb > 1 && lines_z_member().npairs % zlines<N>() != 0) throw EngineError{"ensemble handle: grid too small for the z sweeps"};
+    return dim3((unsigned)(bpm_z<N>() * nb));
   }
   static dim3 grid_pw(long nelem) {
     long g = (nelem + 255) / 256;
@@ -578,23 +599,36 @@ class Engine : public EngineBase {
       if constexpr (zpipe_fits<T, N>()) {
         // persistent warp-private pipelined form (sweeps_zpipe.cuh; measured: 49.7 -> 45.8 us at 256^3,
         // 603 -> 526 us at 512^3, profiles/r2d_zpipe_twldg_ab.txt)
-        const long np = lines_z().npairs;
-        const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());
-        const int cap = nsm * zpipe_ctas<T, N>();
-        LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(ngroups < cap ? ngroups : cap)), dim3(zthreads<N>()),
-           zpipe_smem<T, N>(), zs, lines_z(), ngroups, x, kfield, zo, (const C*)tw[2], done);
+        const long np = lines_z_member().npairs;
+        const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());   // of one member
+        int cap = nsm * zpipe_ctas<T, N>() / nb;
+        if (cap < 1) cap = 1;
+        const int cpm = ngroups < cap ? ngroups : cap;
+        LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), zpipe_smem<T, N>(), zs,
+           lines_z_member(), ngroups, x, kfield, zo, (const C*)tw[2], done, cpm);
       } else {
+        if (nb > 1) throw EngineError{"ensemble handle: this z line length needs the pipelined sweep"};
         LP(tag, kz_deriv2<T, N, ADD, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), zs, lines_z(), x, kfield, zo,
            (const C*)tw[2], done);
       }
     });
   }
-  static RowsS<T> rows_s(const TileS& g, const void* ptr) {
-    return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, g.nchunk};
+  RowsS<T> rows_s(const TileS& g, const void* ptr) const {
+    return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, g.nchunk, g.nchunk * g.n_outer, nreal_m / 2};
   }
-  template <int N> dim3 grid_pipe(int ntiles) const {
-    const int g = nsm * pipe_ctas<T, N>();
-    return dim3((unsigned)(ntiles < g ? ntiles : g));
+  // persistent S kernels: CTAs per member (ntiles = tiles of ONE member); the grid is cpm x members
+  template <int N> int cpm_pipe(int ntiles) const {
+    int g = nsm * pipe_ctas<T, N>() / nb;
+    if (g < 1) g = 1;
+    return ntiles < g ? ntiles : g;
+  }
+  template <int N> dim3 grid_pipe(int ntiles) const { return dim3((unsigned)(cpm_pipe<N>(ntiles) * nb)); }
+  void upload_syms() {
+    std::vector<PcSym<T>> h(nb, sym);
+    if (kavg_per_member)
+      for (int m = 0; m < nb; ++m) { h[m].kxx = kavg_m[3 * m]; h[m].kyy = kavg_m[3 * m + 1]; h[m].kzz = kavg_m[3 * m + 2]; }
+    GLIA_CHECK(rt::h2d(syms_d, h.data(), sizeof(PcSym<T>) * nb, st));
+    GLIA_CHECK(rt::sync(st));
   }
   // one S-geometry D(k D x) sweep on local rows; returns the number of partial-sum blocks
   template <int EPI>
@@ -604,27 +638,30 @@ class Engine : public EngineBase {
     int nblk = 0;
     GLIA_DISPATCH_N(nline, {
       if constexpr (pipe_fits<T, N>()) {
-        const int ntiles = g.nchunk * g.n_outer;
+        const int ntiles = g.nchunk * g.n_outer;   // of one member
         const dim3 gr = grid_pipe<N>(ntiles);
-        nblk = (int)gr.x;
+        const int cpm = cpm_pipe<N>(ntiles);
+        nblk = cpm;                                // partial sums per member
         bool launched = false;
         // slab handles: this sweep consumes what the peers' x sweeps wrote into acc (gate left pending by dapply_dist)
         const PeerGate gate = (G > 1 && gate_pending) ? gate_consumer() : gate_none();
         if constexpr (EPI != EPI_ADD && EPI != EPI_SET) {
           if (acc_extra) {
-            const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk};
+            const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk,
+                               g.nchunk * g.n_outer, nreal_m / 2};
             LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
                st, ntiles, rows_s(g, x), rows_s(g, kfield), a2, rows_s(g, out1), rows_s(g, out2),
-               (const C*)tw_for(nline, g), alpha, pp, done, gate);
+               (const C*)tw_for(nline, g), alpha, pp, done, gate, cpm);
             launched = true;
           }
         }
         if (!launched)
           LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(), st,
              ntiles, rows_s(g, x), rows_s(g, kfield), rows_s(g, acc), rows_s(g, out1), rows_s(g, out2),
-             (const C*)tw_for(nline, g), alpha, pp, done, gate);
+             (const C*)tw_for(nline, g), alpha, pp, done, gate, cpm);
       } else {  // three tiles exceed shared memory (double precision at 512 points): one tile per CTA
         gate_wait_kernel();
+        if (nb > 1) throw EngineError{"ensemble handle: this line length needs the pipelined sweeps"};
         if (acc_extra) throw EngineError{"internal: two-field accumulator needs the pipelined sweep"};
         if (keep_x && smem_s2<N>() > 227 * 1024)
           throw EngineError{"512-point lines in double precision: the operatorA sweep does not fit shared memory"};
@@ -671,7 +708,7 @@ class Engine : public EngineBase {
         if (!overlapped) { gate.signal_out = 0; gate_pending = 0; }
         L("kx_deriv2_dist", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, gx,
           block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)const_cast<T*>(kpen), txd}, ra, ra, ra,
-          (const C*)tw[0], (T)0, (double*)nullptr, done, gate);
+          (const C*)tw[0], (T)0, (double*)nullptr, done, gate, (int)gx.x);
         if (!overlapped) barrier();
       } else {
         barrier();
@@ -702,23 +739,24 @@ class Engine : public EngineBase {
     int nblk = 0;
     if (wv) {
       GLIA_DISPATCH_N(n[2], LP("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                         lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done));
+                                         lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done,
+                                         bpm_z<N>()));
     } else {
       GLIA_DISPATCH_N(n[2], LP("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
                                          lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
-                                         (const C*)tw[2], done));
+                                         (const C*)tw[2], done, bpm_z<N>()));
     }
     GLIA_DISPATCH_N(n[1], {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
 #if !defined(GLIA_SIMT_EMU)
-        if (use_tma && tma_map()) {
+        if (use_tma && nb == 1 && tma_map()) {
           LP("ks_c2c.y", ks_c2c_tma<T, N, -1>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, ty.nchunk,
              tmap_shat, (const C*)tw[1], done);
         } else
 #endif
         LP("ks_c2c.y", ks_c2c_pipe<T, N, -1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, gate_none());
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, gate_none(), cpm_pipe<N>(ntiles));
       } else {
         LP("ks_c2c.y", ks_c2c<T, N, -1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
            (const C*)tw[1], done);
@@ -731,7 +769,8 @@ class Engine : public EngineBase {
         if constexpr (pipe_fits<T, N>()) {  // gated like the D-apply's x sweep; the inverse y sweep below is the consumer
           const int ntiles = txd.nchunk * txd.n_outer;
           L("kx_pc_dist", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], done, gate_xsweep());
+            RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], (const PcSym<T>*)syms_d, n[1], done, gate_xsweep(),
+            cpm_pipe<N>(ntiles));
         } else {
           barrier();
           L("kx_pc_dist", kx_pc_dist<T, N>, grid_xd(txd), block_s<N>(), smem_s<N>(), st, txd, sr, (const C*)tw[0], sym, n[1],
@@ -744,8 +783,10 @@ class Engine : public EngineBase {
         if constexpr (pipe_fits<T, N>()) {
           const int ntiles = tx.nchunk * tx.n_outer;
           LP("ks_pc", ks_pc_pipe<T, N, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-            rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], sym, n[1], done, gate_none());
+            rows_s(tx, shat), rows_s(tx, shat), (const C*)tw[0], (const PcSym<T>*)syms_d, n[1], done, gate_none(),
+            cpm_pipe<N>(ntiles));
         } else {
+          if (nb > 1) throw EngineError{"ensemble handle: this line length needs the pipelined sweeps"};
           L("ks_pc", ks_pc<T, N>, grid_s(tx), block_s<N>(), smem_s<N>(), st, tx, shat, (const C*)tw[0], sym, n[1], done);
         }
       });
@@ -754,13 +795,14 @@ class Engine : public EngineBase {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
 #if !defined(GLIA_SIMT_EMU)
-        if (use_tma && tma_map()) {
+        if (use_tma && nb == 1 && tma_map()) {
           LP("ks_c2c.y", ks_c2c_tma<T, N, +1>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles, ty.nchunk,
              tmap_shat, (const C*)tw[1], done);
         } else
 #endif
         LP("ks_c2c.y", ks_c2c_pipe<T, N, +1, RowsS<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, (G > 1 && gate_pending) ? gate_consumer() : gate_none());
+           rows_s(ty, shat), rows_s(ty, shat), (const C*)tw[1], done, (G > 1 && gate_pending) ? gate_consumer() : gate_none(),
+           cpm_pipe<N>(ntiles));
       } else {
         gate_wait_kernel();
         LP("ks_c2c.y", ks_c2c<T, N, +1>, grid_s(ty), block_s<N>(), smem_s<N>(), st, ty, (const C*)shat, shat,
@@ -768,19 +810,20 @@ class Engine : public EngineBase {
       }
     });
     GLIA_DISPATCH_N(n[2], {
-      nblk = (int)grid_z<N>().x;
+      nblk = bpm_z<N>();   // partial sums per member
       if (zout && want_rz)
         LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
-           lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done);
+           lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, bpm_z<N>());
       else
         LP(zout ? "kz_c2r" : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(),
-           (const C*)shat, zout, (const T*)nullptr, pp, (const C*)tw[2], done);
+           (const C*)shat, zout, (const T*)nullptr, pp, (const C*)tw[2], done, bpm_z<N>());
     });
     return nblk;
   }
 
   // ------------------------------------------------------------ L0 API ----
   void gradient(T* gx, T* gy, T* gz, const T* x, int mask) {
+    need_one_member("glia_rd_gradient");
     const TileS ty = tile_y(), tx = tile_x();
     if ((mask & 4) && gz) {
       GLIA_DISPATCH_N(n[2], L("kz_deriv1", kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
@@ -805,6 +848,7 @@ class Engine : public EngineBase {
     sync();
   }
   void divergence(T* div, const T* dx, const T* dy, const T* dz) {
+    need_one_member("glia_rd_divergence");
     const TileS ty = tile_y(), tx = tile_x();
     T* out = G > 1 ? acc : div;
     GLIA_DISPATCH_N(n[2], L("kz_deriv1", kz_deriv1<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
@@ -830,13 +874,15 @@ class Engine : public EngineBase {
   void set_diffusion(const T* k, const double ka[3], double kscale) {
     GLIA_CHECK(rt::copy(kf, k, sizeof(T) * nreal, st));
     for (int i = 0; i < 3; ++i) kavg[i] = (T)ka[i];
+    kavg_per_member = false;
     k_scale = (T)kscale;
     if (G > 1) build_pencil(kf, kT);
     sync();
   }
-  void field_sum4(const T* t, const T* m0, const T* m1, const T* m2, double out[4]) {
-    const dim3 g = grid_pw(nreal);
-    L("k_dot3", k_dot3<T>, g, dim3(256), 0, st, nreal, t, m0, m1, m2, part(0));
+  void field_sum4(const T* t, const T* m0, const T* m1, const T* m2, double out[4], long nelem = -1) {
+    if (nelem < 0) nelem = nreal;
+    const dim3 g = grid_pw(nelem);
+    L("k_dot3", k_dot3<T>, g, dim3(256), 0, st, nelem, t, m0, m1, m2, part(0));
     L("k_sum4", k_sum4, dim3(1), dim3(256), 0, st, (const double*)part(0), (int)g.x, scal + 8, comm,
       G > 1 ? next_epoch() : 0u, rseq++);
     GLIA_CHECK(rt::d2h(h_out, scal + 8, sizeof(double) * 4, st));
@@ -861,6 +907,7 @@ class Engine : public EngineBase {
     const T favg = (T)filter_sum;
     const T kav = ksum * ((T)1.0 / favg);
     kavg[0] = kavg[1] = kavg[2] = kav;
+    kavg_per_member = false;
     if (G > 1) { build_pencil(kf, kT); sync(); }
   }
   void set_reaction_tissue(const T* wm, const T* gm, const T* csf, double rs, double rgm, double rglm) {
@@ -871,6 +918,37 @@ class Engine : public EngineBase {
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_gm, gm, (T)0, (const T*)nullptr);
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_wm, wm, (T)1, (const T*)rho);
     L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal, rho, dr_glm, csf, (T)1, (const T*)rho);
+    sync();
+  }
+  // Ensemble handles (BASELINE config 5): one set of tissue maps (ONE member's fields), a (kappa, rho) pair per
+  // member.  DiffCoef::setValues / ReacCoef::setValues per member (src/mat/DiffCoef.cpp:77-131, src/mat/ReacCoef.cpp:
+  // 13-38), k-bar per member for the preconditioner symbol.
+  void set_coefficients_batch(const T* wm, const T* gm, const T* csf, const double* ks, double kgm, double kglm,
+                              double filter_sum, const double* rs, double rgm, double rglm) {
+    const dim3 g = grid_pw(nreal_m);
+    for (int m = 0; m < nb; ++m) {
+      T* km = kf + (size_t)m * nreal_m;
+      T* rm = rho + (size_t)m * nreal_m;
+      T dk_gm = (T)ks[m] * (T)kgm, dk_wm = (T)ks[m], dk_glm = (T)ks[m] * (T)kglm;
+      if (dk_gm <= 0) dk_gm = 0;
+      if (dk_glm <= 0) dk_glm = 0;
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, km, dk_gm, gm, (T)0, (const T*)nullptr);
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, km, dk_wm, wm, (T)1, (const T*)km);
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, km, dk_glm, csf, (T)1, (const T*)km);
+      double s4[4];
+      field_sum4(km, nullptr, nullptr, nullptr, s4, nreal_m);
+      const T kav = (T)s4[3] * ((T)1.0 / (T)filter_sum);
+      kavg_m[3 * m] = kavg_m[3 * m + 1] = kavg_m[3 * m + 2] = kav;
+      T dr_gm = (T)rs[m] * (T)rgm, dr_wm = (T)rs[m], dr_glm = (T)rs[m] * (T)rglm;
+      if (dr_gm <= 0) dr_gm = 0;
+      if (dr_glm <= 0) dr_glm = 0;
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, rm, dr_gm, gm, (T)0, (const T*)nullptr);
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, rm, dr_wm, wm, (T)1, (const T*)rm);
+      L("k_axpby", k_axpby<T>, g, dim3(256), 0, st, nreal_m, rm, dr_glm, csf, (T)1, (const T*)rm);
+    }
+    k_scale = (T)ks[0];
+    kavg[0] = kavg[1] = kavg[2] = kavg_m[0];
+    kavg_per_member = true;
     sync();
   }
   // mass-effect style refresh of rho(x) and k(x) between time steps.  Like the reference it leaves the
@@ -884,7 +962,7 @@ class Engine : public EngineBase {
     sync();
   }
   void apply_D(T* dc, const T* c, bool secondary) {
-    const T* src = c;
+    const T* src = c;   // (an ensemble handle applies every member's own k to its member of c)
     if (dc == c || (G > 1 && !in_arena(c))) {  // the reference allows aliasing (PdeOperators.cpp:210)
       GLIA_CHECK(rt::copy(work11, c, sizeof(T) * nreal, st));
       src = work11;
@@ -899,10 +977,11 @@ class Engine : public EngineBase {
     sym.kxx = kavg[0];
     sym.kyy = kavg[1];
     sym.kzz = kavg[2];
+    upload_syms();
   }
 
   void fetch_iscal() {
-    GLIA_CHECK(rt::d2h(h_iscal, iscal, sizeof(int) * I_NISCAL, st));
+    GLIA_CHECK(rt::d2h(h_iscal, iscal, sizeof(int) * I_NISCAL * nb, st));
     sync();  // (throws if a peer wait timed out)
   }
 
@@ -911,13 +990,13 @@ class Engine : public EngineBase {
     const int* done = iscal + I_DONE;
     const T alph = (T)(-1.0 / 2.0 * (double)dt_solve);
     const int nb1 = dapply<EPI_MATVEC>(p, kf, alph, w, nullptr, part(0), done);
-    LP("k_pcg_alpha", k_pcg_alpha<T>, dim3(1), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal, comm,
+    LP("k_pcg_alpha", k_pcg_alpha<T>, dim3(nb), dim3(256), 0, st, (const double*)part(0), nb1, scal, iscal, comm,
       G > 1 ? next_epoch() : 0u, rseq++);
     const int nb2 = pc_apply(r, w, z, true, part(1), done);
-    LP("k_pcg_beta", k_pcg_beta<T>, dim3(1), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
+    LP("k_pcg_beta", k_pcg_beta<T>, dim3(nb), dim3(256), 0, st, (const double*)part(1), nb2, scal, iscal, maxit, dtol,
       comm, G > 1 ? next_epoch() : 0u, rseq++);
-    LP("k_cg_update", k_cg_update<T>, grid_pw(nreal), dim3(256), 0, st, nreal, (const T*)(it == 1 ? xin : x), x, p,
-       (const T*)z, (const double*)scal, (const int*)iscal, it);
+    LP("k_cg_update", k_cg_update<T>, dim3(grid_pw(nreal_m).x, nb), dim3(256), 0, st, nreal_m,
+       (const T*)(it == 1 ? xin : x), x, p, (const T*)z, (const double*)scal, (const int*)iscal, it);
   }
 
   // DiffusionSolver::solve.  Asynchronous up to the convergence read-back.  With `xin` the solve starts from that
@@ -942,24 +1021,36 @@ class Engine : public EngineBase {
     dapply<EPI_RHS>(src, kf, alph, b, r, nullptr, nullptr);
     const int nb0 = pc_apply(b, nullptr, nullptr, false, part(2), nullptr);
     const int nb1 = pc_apply(r, nullptr, p, true, part(1), nullptr);
-    L("k_pcg_init", k_pcg_init, dim3(1), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
+    L("k_pcg_init", k_pcg_init, dim3(nb), dim3(256), 0, st, (const double*)part(2), nb0, (const double*)part(1), nb1,
                  scal, iscal, rtol, abstol, comm, G > 1 ? next_epoch() : 0u, rseq++);
     int it = 0;
-    // speculate: enqueue as many iterations as the previous solve needed, then look
+    // speculate: enqueue as many iterations as the previous solve needed, then look.  Ensemble handles iterate until
+    // EVERY member has converged; the kernels of a converged member's CTAs return at once.
     int burst = its_guess < 1 ? 1 : its_guess;
     for (;;) {
       for (int j = 0; j < burst; ++j) enqueue_iteration(x, src, dts, ++it);
       fetch_iscal();
-      if (h_iscal[I_DONE]) break;
+      bool all_done = true;
+      for (int m = 0; m < nb; ++m) all_done = all_done && h_iscal[m * I_NISCAL + I_DONE];
+      if (all_done) break;
       burst = 1;
       if (it > maxit + 1) break;
     }
-    const int its = h_iscal[I_ITS];
-    if (h_iscal[I_REASON] < 0 && h_iscal[I_REASON] != KSP_DIVERGED_ITS)
-      throw EngineError{"KSP diverged, reason " + std::to_string(h_iscal[I_REASON])};
-    if (its == 0 && xin) GLIA_CHECK(rt::copy(x, xin, sizeof(T) * nreal, st));  // converged at the iteration-0 test
-    its_guess = its;
-    return its;
+    int its_max = 0, its_sum = 0;
+    for (int m = 0; m < nb; ++m) {
+      const int* hi = h_iscal + m * I_NISCAL;
+      if (hi[I_REASON] < 0 && hi[I_REASON] != KSP_DIVERGED_ITS)
+        throw EngineError{"KSP diverged, reason " + std::to_string(hi[I_REASON]) + " (member " + std::to_string(m) + ")"};
+      its_m[m] = hi[I_ITS];
+      its_acc[m] += hi[I_ITS];
+      its_sum += hi[I_ITS];
+      if (hi[I_ITS] > its_max) its_max = hi[I_ITS];
+      // a member that converged at the iteration-0 test never ran the update that moves xin into x
+      if (hi[I_ITS] == 0 && xin)
+        GLIA_CHECK(rt::copy(x + (size_t)m * nreal_m, xin + (size_t)m * nreal_m, sizeof(T) * nreal_m, st));
+    }
+    its_guess = its_max;
+    return its_sum;   // one member: ksp_itr_; an ensemble: the sum over its members (per member: batch_iterations())
   }
 
   // ------------------------------------------------------------ L2a API ----
@@ -1007,6 +1098,8 @@ class Engine : public EngineBase {
   }
   int solve_state(const T* c0, T* cT, int linearized) {
     if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
+    if (linearized == 2) need_one_member("solve_state(2)");
+    std::fill(its_acc.begin(), its_acc.end(), 0);
     int total = 0;
     const double dth = (double)dt / 2.0;
     if (linearized == 0) {
@@ -1037,6 +1130,7 @@ class Engine : public EngineBase {
   }
   int solve_adjoint(const T* pT, T* p0out, int linearized, int adjoint_store) {
     if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
+    std::fill(its_acc.begin(), its_acc.end(), 0);
     GLIA_CHECK(rt::copy(p_0, pT, sizeof(T) * nreal, st));
     if (linearized == 1) GLIA_CHECK(rt::copy(hist(1, nt), p_0, sizeof(T) * nreal, st));
     int total = 0;
@@ -1062,6 +1156,7 @@ class Engine : public EngineBase {
 
   // ------------------------------------------------------------ L2b API ----
   void grad_kappa_rho(const T* wm, const T* gm, const T* csf, double out[6]) {
+    need_one_member("glia_rd_grad_kappa_rho");
     if (nt <= 0 || !c_hist) throw EngineError{"resize_history() first"};
     GLIA_CHECK(rt::zero(Tk, sizeof(T) * nreal, st));
     GLIA_CHECK(rt::zero(Tr, sizeof(T) * nreal, st));
@@ -1198,7 +1293,8 @@ class Engine : public EngineBase {
         GLIA_DISPATCH_N(n[0], {
           if constexpr (pipe_fits<T, N>())
             L("probe", ks_pc_pipe<T, N, RowsX<T>>, grid_pipe<N>(ntiles), block_s<N>(), pipe_smem<T, N>(), st, ntiles,
-              RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], sym, n[1], (const int*)nullptr, gate_none());
+              RowsX<T>{sr, txd}, RowsX<T>{sw, txd}, (const C*)tw[0], (const PcSym<T>*)syms_d, n[1], (const int*)nullptr,
+              gate_none(), cpm_pipe<N>(ntiles));
         });
       } else {
         const PeerRows<T> xr = rows(p, 1), ar = rows(acc, 2);
@@ -1207,7 +1303,7 @@ class Engine : public EngineBase {
           if constexpr (pipe_fits<T, N>())
             L("probe", ks_deriv2_pipe<T, N, EPI_SET, RowsX<T>, RowsPen<T>, RowsX<T>, RowsX<T>>, grid_pipe<N>(ntiles),
               block_s<N>(), pipe_smem<T, N>(), st, ntiles, rx, RowsPen<T>{(C*)kT, txd}, ra, ra, ra, (const C*)tw[0], (T)0,
-              (double*)nullptr, (const int*)nullptr, gate_none());
+              (double*)nullptr, (const int*)nullptr, gate_none(), cpm_pipe<N>(ntiles));
         });
       }
     }
@@ -1256,6 +1352,10 @@ class Engine : public EngineBase {
   }
   void need_single(const char* what) const {
     if (G > 1) throw EngineError{std::string(what) + ": single-GPU handles only (slab handles take c(0) as a field)"};
+    if (nb > 1) throw EngineError{std::string(what) + ": not available on ensemble handles"};
+  }
+  void need_one_member(const char* what) const {
+    if (nb > 1) throw EngineError{std::string(what) + ": not available on ensemble handles (nbatch > 1)"};
   }
   // SpectralOperators::weierstrassSmoother (src/grad/SpectralOperators.cpp:263-381); out may alias in
   void smooth(T* out, const T* in, double sigma) {
@@ -1456,10 +1556,12 @@ class Engine : public EngineBase {
   void v_make_current() override { make_current(); }
   void v_fft_r2c(const void* f, void* fhat) override {
     if (G > 1) throw EngineError{"glia_rd_fft_r2c: the stand-alone 3-D FFT is single-GPU; slab handles transform inside the sweeps"};
+    need_one_member("glia_rd_fft_r2c");
     fft3d_r2c(*this, (const T*)f, (C*)fhat);
   }
   void v_fft_c2r(const void* fhat, void* f) override {
     if (G > 1) throw EngineError{"glia_rd_fft_c2r: the stand-alone 3-D FFT is single-GPU; slab handles transform inside the sweeps"};
+    need_one_member("glia_rd_fft_c2r");
     fft3d_c2r(*this, (const C*)fhat, (T*)f);
   }
   void v_ipc_export(int which, unsigned char* out) override { ipc_export(which, out); }
@@ -1467,6 +1569,14 @@ class Engine : public EngineBase {
   void v_ipc_disconnect(int which) override { ipc_disconnect(which); }
   void v_wait_stream(void* producer) override { GLIA_CHECK(rt::stream_wait_stream(st, (cudaStream_t)(intptr_t)producer)); }
   void v_set_order(int o) override { order = o; }
+  int v_nbatch() const override { return nb; }
+  void v_batch_iterations(int* out, int accumulated) override {
+    for (int m = 0; m < nb; ++m) out[m] = accumulated ? its_acc[m] : its_m[m];
+  }
+  void v_set_coefficients_batch(const void* wm, const void* gm, const void* csf, const double* ks, double kgm, double kglm,
+                                double fsum, const double* rs, double rgm, double rglm) override {
+    set_coefficients_batch((const T*)wm, (const T*)gm, (const T*)csf, ks, kgm, kglm, fsum, rs, rgm, rglm);
+  }
   void v_set_two_snapshot(const void* d0_, const void* obs0_) override {
     two_snap = d0_ != nullptr;
     has_obs0 = two_snap && obs0_ != nullptr;

@@ -24,6 +24,10 @@ class EngineBase {
   virtual void v_ipc_disconnect(int which) = 0;
   virtual void v_wait_stream(void* producer_stream) = 0;
   virtual void v_set_order(int order) = 0;
+  virtual int v_nbatch() const = 0;
+  virtual void v_batch_iterations(int* out, int accumulated) = 0;
+  virtual void v_set_coefficients_batch(const void* wm, const void* gm, const void* csf, const double* k_scale, double kgm,
+                                        double kglm, double filter_sum, const double* rho_scale, double rgm, double rglm) = 0;
   virtual void v_set_two_snapshot(const void* d0, const void* obs0) = 0;
   virtual void v_fft_r2c(const void* f, void* fhat) = 0;
   virtual void v_fft_c2r(const void* fhat, void* f) = 0;
@@ -69,7 +73,7 @@ class EngineBase {
   virtual void v_forward_adjoint(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
   virtual void v_forward_adjoint_host(const void* c0, const void* d1, void* cT, void* p0, int* ks, int* ka) = 0;
 };
-EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx, int rank, int nranks);
-EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks);
+EngineBase* make_engine_f32(const int n[3], int device, double dt_ctx, int rank, int nranks, int nbatch);
+EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks, int nbatch);
 
 }  // namespace glia

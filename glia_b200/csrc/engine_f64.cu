@@ -2,7 +2,7 @@
 #include "engine.cuh"
 #include "spectral3d.cuh"
 namespace glia {
-EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks) {
-  return new Engine<double>(n, device, dt_ctx, rank, nranks);
+EngineBase* make_engine_f64(const int n[3], int device, double dt_ctx, int rank, int nranks, int nbatch) {
+  return new Engine<double>(n, device, dt_ctx, rank, nranks, nbatch);
 }
 }  // namespace glia

@@ -58,6 +58,17 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// Ensemble batching (BASELINE config 5: independent members, "batched one or more per GPU").  A handle may carry NB
+// members, every field laid out [NB][n0][n1][n2].  Lines along z and y never leave an x-plane, so the Z sweeps and the
+// y sweeps see a batch as a taller grid; only the x sweeps address a member explicitly.  A CTA always works for ONE
+// member (member = blockIdx.x / cpm, cpm = CTAs per member): its partial sums belong to that member, and the CTAs of
+// a member whose PCG has converged leave at once.  Per-member PCG state sits DONE_STRIDE ints / SCAL_STRIDE doubles
+// apart (pointwise.cuh: I_NISCAL, S_NSCAL).
+static constexpr int DONE_STRIDE = 8, SCAL_STRIDE = 16;
+__device__ __forceinline__ const int* member_done(const int* done, int member) {
+  return done ? done + (size_t)member * DONE_STRIDE : done;
+}
+
 // Where a sweep kernel waits for its predecessor and tests the PCG's `done` flag (written by an earlier
 // kernel, so only readable after the wait).  Measured on the B200 (gpurun_out/r1l_*, profiles/r1l_pdl_matrix.txt):
 // waiting AFTER the twiddle registers are loaded is the faster place for lines up to 256 points

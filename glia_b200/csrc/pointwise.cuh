@@ -14,6 +14,7 @@ __device__ __forceinline__ bool g_isinf(T x) { return x == x && (x - x) != (x - 
 // ---- device-resident PCG state (one block per solver handle) --------------
 enum { S_BETA = 0, S_BETAOLD, S_A, S_B, S_DP, S_RNORM0, S_TTOL, S_DPI, S_NSCAL = 16 };
 enum { I_ITS = 0, I_DONE, I_TOTAL, I_REASON, I_COMM_ERR, I_NISCAL = 8 };
+static_assert(I_NISCAL == DONE_STRIDE && S_NSCAL == SCAL_STRIDE, "per-member strides of the PCG state (fft_core.cuh)");
 // reasons follow PETSc's KSPConvergedReason values
 enum { KSP_CONVERGED_RTOL = 2, KSP_CONVERGED_ATOL = 3, KSP_DIVERGED_ITS = -3, KSP_DIVERGED_DTOL = -4,
        KSP_DIVERGED_NANORINF = -9, KSP_DIVERGED_INDEFINITE_MAT = -10 };
@@ -94,8 +95,13 @@ __device__ __forceinline__ void pcg_beta_finish(const double (&rz)[2], double* s
 }
 // KSPConvergedDefault at iteration 0 with a non-zero initial guess:
 //   rnorm0 = ||M^-1 b|| (or dp if that is 0), ttol = max(rtol*rnorm0, abstol), test dp <= ttol.
+// (one CTA per ensemble member: blockIdx.x selects the member's partial sums and state block)
 static __global__ void k_pcg_init(const double* pb, int nb, const double* prz, int nrz, double* scal, int* iscal,
                            double rtol, double abstol, Comm comm, unsigned epoch, unsigned seq) {
+  pb += (size_t)blockIdx.x * nb * 2;
+  prz += (size_t)blockIdx.x * nrz * 2;
+  scal += (size_t)blockIdx.x * S_NSCAL;
+  iscal += (size_t)blockIdx.x * I_NISCAL;
   double b[2], rz[2];
   sum_partials<2>(pb, nb, b);
   sum_partials<2>(prz, nrz, rz);
@@ -125,6 +131,9 @@ template <typename T>
 __global__ void k_pcg_alpha(const double* ppw, int n, double* scal, int* iscal, Comm comm, unsigned epoch,
                             unsigned seq) {
   pdl_wait();
+  ppw += (size_t)blockIdx.x * n;
+  scal += (size_t)blockIdx.x * S_NSCAL;
+  iscal += (size_t)blockIdx.x * I_NISCAL;
   if (iscal[I_DONE]) return;
   double d[1];
   sum_partials<1>(ppw, n, d);
@@ -137,6 +146,9 @@ template <typename T>
 __global__ void k_pcg_beta(const double* prz, int n, double* scal, int* iscal, int maxit, double dtol, Comm comm,
                            unsigned epoch, unsigned seq) {
   pdl_wait();
+  prz += (size_t)blockIdx.x * n * 2;
+  scal += (size_t)blockIdx.x * S_NSCAL;
+  iscal += (size_t)blockIdx.x * I_NISCAL;
   if (iscal[I_DONE]) return;
   double rz[2];
   sum_partials<2>(prz, n, rz);
@@ -155,7 +167,12 @@ template <typename T>
 __global__ void k_cg_update(long n, const T* xin, T* x, T* p, const T* __restrict__ z, const double* scal,
                             const int* iscal, int it) {
   pdl_wait();
+  // blockIdx.y = ensemble member; n = elements of ONE member
+  scal += (size_t)blockIdx.y * S_NSCAL;
+  iscal += (size_t)blockIdx.y * I_NISCAL;
   if (it > iscal[I_ITS]) return;
+  const size_t mo = (size_t)blockIdx.y * (size_t)n;
+  xin += mo; x += mo; p += mo; z += mo;
   const T a = (T)scal[S_A], b = (T)scal[S_B];
   const int done = iscal[I_DONE];
   const long stride = (long)gridDim.x * blockDim.x;

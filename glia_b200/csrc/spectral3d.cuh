@@ -54,7 +54,7 @@ void fft3d_r2c(Engine<T>& E, const T* f, cplx<T>* fhat) {
   GLIA_DISPATCH_N(E.n[2], E.L("kz_r2c", kz_r2c<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
                                        Engine<T>::template smem_z<N>(), E.st, E.lines_z(), const_cast<T*>(f),
                                        (const T*)nullptr, (const double*)nullptr, E.shat, (const C*)E.tw[2],
-                                       (const int*)nullptr));
+                                       (const int*)nullptr, E.template bpm_z<N>()));
   GLIA_DISPATCH_N(E.n[1], E.L("ks_c2c", ks_c2c<T, N, -1>, Engine<T>::grid_s(ty), Engine<T>::template block_s<N>(),
                                        Engine<T>::template smem_s<N>(), E.st, ty, (const C*)E.shat, E.shat,
                                        (const C*)E.tw[1], (const int*)nullptr));
@@ -79,7 +79,8 @@ void fft3d_c2r(Engine<T>& E, const cplx<T>* fhat, T* f) {
                                        (const C*)E.tw[1], (const int*)nullptr));
   GLIA_DISPATCH_N(E.n[2], E.L("kz_c2r", kz_c2r<T, N, 0>, E.template grid_z<N>(), dim3(zthreads<N>()),
                                        Engine<T>::template smem_z<N>(), E.st, E.lines_z(), (const C*)E.shat, f,
-                                       (const T*)nullptr, (double*)nullptr, (const C*)E.tw[2], (const int*)nullptr));
+                                       (const T*)nullptr, (double*)nullptr, (const C*)E.tw[2], (const int*)nullptr,
+                                       E.template bpm_z<N>()));
   E.sync();
 }
 

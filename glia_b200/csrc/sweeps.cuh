@@ -554,7 +554,9 @@ kz_gradprod(LinesZ ln, const T* __restrict__ c, const T* __restrict__ p, T* Tk, 
 template <typename T, int N, int PRO>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal_a, cplx<T>* shat,
-       const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+       const cplx<T>* __restrict__ twt, const int* __restrict__ done, int bpm) {
+  const int member = blockIdx.x / bpm;  // bpm = CTAs per ensemble member
+  done = member_done(done, member);
   GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;
@@ -567,7 +569,7 @@ kz_r2c(LinesZ ln, T* r, const T* __restrict__ w, const double* __restrict__ scal
   typename ZSync<F::TPL>::type sy;
   const long la = z.pair * 2 * N, lb = la + N;
   T aa = (T)0;
-  if (PRO) aa = (T)(*scal_a);
+  if (PRO) aa = (T)(scal_a[(size_t)member * SCAL_STRIDE]);
   cplx<T> v[E];
   GLIA_UNROLL
   for (int g = 0; g < F::Gp(0); ++g)
@@ -625,7 +627,8 @@ __host__ __device__ constexpr size_t smem_z_rstage() { return (size_t)zlines<N>(
 template <typename T, int N, int EPI>
 __global__ void __launch_bounds__(zthreads<N>())
 kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict__ r, double* partial,
-       const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+       const cplx<T>* __restrict__ twt, const int* __restrict__ done, int bpm) {
+  done = member_done(done, blockIdx.x / bpm);  // bpm = CTAs per ensemble member; partial[blockIdx.x] is the member's
   GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E;

@@ -36,7 +36,10 @@ __host__ __device__ constexpr int zpipe_ctas() {
 template <typename T, int N, int ADD>
 __global__ void __launch_bounds__(zthreads<N>(), zpipe_ctas<T, N>())
 kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restrict__ kf, T* acc,
-               const cplx<T>* __restrict__ twt, const int* __restrict__ done) {
+               const cplx<T>* __restrict__ twt, const int* __restrict__ done, int cpm) {
+  // ngroups = line-pair groups of ONE ensemble member, cpm = CTAs per member (fft_core.cuh: ensemble batching)
+  const int member = blockIdx.x / cpm, cl = blockIdx.x % cpm;
+  done = member_done(done, member);
   GLIA_PDL_ENTRY_EARLY(done);
   using F = LineFft<T, N, zplan<N>()>;
   constexpr int E = F::E, TPL = F::TPL, LPC = zlines<N>();
@@ -55,9 +58,10 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
   constexpr int CH = (2 * N * (int)sizeof(T)) / 16;  // 16-byte chunks of one pair's two lines
   static_assert(CH % TPL == 0, "chunks per thread");
 
+  const long pair0 = (long)member * ln.npairs;  // ln.npairs = line pairs of one member
   auto pair_of = [&](int group) -> long {
     long p = (long)group * LPC + lp;
-    return p < ln.npairs ? p : ln.npairs - 1;  // ragged tail: re-do the last pair, stores predicated
+    return pair0 + (p < ln.npairs ? p : ln.npairs - 1);  // ragged tail: re-do the last pair, stores predicated
   };
   auto prefetch = [&](T* stage, const T* field, int group) {
     const char* src = reinterpret_cast<const char*>(field + pair_of(group) * 2 * N);
@@ -68,12 +72,12 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
     }
   };
 
-  int group = blockIdx.x, s = 0;
+  int group = cl, s = 0;
   if (group < ngroups) prefetch(stage0, x, group);
   cp_async_commit();
-  for (; group < ngroups; group += gridDim.x, s ^= 1) {
+  for (; group < ngroups; group += cpm, s ^= 1) {
     T* st = stage0 + (size_t)s * (2 * N);
-    const int next = group + gridDim.x;
+    const int next = group + cpm;
     if (next < ngroups) prefetch(stage0 + (size_t)(s ^ 1) * (2 * N), x, next);
     cp_async_commit();
     const long pair = pair_of(group);

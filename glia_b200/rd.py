@@ -37,7 +37,8 @@ class RDHandle:
     ``bytes -> list[bytes]`` in rank order, e.g. built on ``torch.distributed.all_gather_object``
     -- carries the 64-byte IPC handles between the ranks at set-up."""
 
-    def __init__(self, n, precision="f32", device=0, dt_ctx=0.5, lib_path=None, rank=0, nranks=1, all_gather=None):
+    def __init__(self, n, precision="f32", device=0, dt_ctx=0.5, lib_path=None, rank=0, nranks=1, all_gather=None,
+                 nbatch=1):
         self.lib = _capi.load_library(lib_path)
         self.n = tuple(int(v) for v in (n if hasattr(n, "__len__") else (n, n, n)))
         self.precision = {"f32": 4, "f64": 8, 4: 4, 8: 8}[precision]
@@ -47,8 +48,13 @@ class RDHandle:
             raise ValueError("a slab handle needs all_gather(bytes) -> list[bytes] to exchange its IPC handles")
         self._h = C.c_void_p()
         arr = (C.c_int * 3)(*self.n)
-        rc = self.lib.glia_rd_create_slab(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx),
-                                          self.rank, self.nranks)
+        self.nbatch = int(nbatch)
+        if self.nbatch > 1:   # ensemble handle: fields are [nbatch][n0][n1][n2]
+            rc = self.lib.glia_rd_create_batch(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx),
+                                               self.nbatch)
+        else:
+            rc = self.lib.glia_rd_create_slab(C.byref(self._h), arr, self.precision, int(device), float(dt_ctx),
+                                              self.rank, self.nranks)
         if rc != 0:
             msg = self.lib.glia_rd_last_error(self._h).decode() if self._h else "create failed"
             if self._h:
@@ -104,7 +110,7 @@ class RDHandle:
 
     @property
     def nreal(self):
-        return self.n[0] * self.n[1] * self.n[2] // self.nranks
+        return self.n[0] * self.n[1] * self.n[2] // self.nranks * getattr(self, "nbatch", 1)
 
     @property
     def launch_count(self):
@@ -145,6 +151,19 @@ class RDHandle:
     def set_reaction_tissue(self, wm, gm, csf, rho_scale, r_gm_wm, r_glm_wm):
         self._ck(self.lib.glia_rd_set_reaction_tissue(self._h, _ptr(wm), _ptr(gm), _ptr(csf), float(rho_scale),
                                                       float(r_gm_wm), float(r_glm_wm)))
+
+    def set_coefficients_batch(self, wm, gm, csf, k_scales, k_gm_wm, k_glm_wm, filter_sum, rho_scales, r_gm_wm, r_glm_wm):
+        """Ensemble handle: one (kappa, rho) pair per member over ONE member's tissue maps."""
+        ks = (C.c_double * self.nbatch)(*[float(v) for v in k_scales])
+        rs = (C.c_double * self.nbatch)(*[float(v) for v in rho_scales])
+        self._ck(self.lib.glia_rd_set_coefficients_batch(self._h, _ptr(wm), _ptr(gm), _ptr(csf), ks, float(k_gm_wm),
+                                                         float(k_glm_wm), float(filter_sum), rs, float(r_gm_wm),
+                                                         float(r_glm_wm)))
+
+    def batch_iterations(self, accumulated=True):
+        out = (C.c_int * self.nbatch)()
+        self._ck(self.lib.glia_rd_batch_iterations(self._h, out, int(bool(accumulated))))
+        return list(out)
 
     def update_reac_diff(self, bg, gm, vt, csf, rho_scale, k_scale, gm_r_scale, gm_k_scale):
         """PdeOperatorsMassEffect::updateReacAndDiffCoefficients (src/pde/PdeOperatorsMassEffect.cpp:98-138)."""

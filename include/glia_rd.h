@@ -62,6 +62,22 @@ int glia_rd_create(glia_rd_t** h, const int n[3], int precision, int device, dou
  * is collective over the ranks (same calls, same order), like the MPI reference. */
 int glia_rd_create_slab(glia_rd_t** h, const int n[3], int precision, int device, double dt_ctx, int rank,
                         int nranks);
+/* Ensemble handle (BASELINE config 5; the reference runs such ensembles as one process per member,
+ * scripts/gridcont/run_sparsetil_multilevel_multigpu.py:25-135): `nbatch` INDEPENDENT members share one handle and one
+ * set of kernel launches.  Every field argument is then [nbatch][n0][n1][n2] (member-major); each member has its own
+ * k(x), rho(x), k-bar, PCG state and iteration count (a converged member stops while the others continue, exactly
+ * as nbatch separate handles would).  Available on such a handle: the coefficient setters (glia_rd_set_coefficients_batch
+ * for a (kappa, rho) pair per member over shared tissue maps; the plain setters take batch-sized fields), prec_factor,
+ * diffusion_solve, reaction, apply_D, resize_history / history, solve_state(0 | 1), solve_adjoint, forward_adjoint.
+ * The int iteration counts these return are sums over the members; glia_rd_batch_iterations gives them per member
+ * (accumulated = 0: the last diffusion solve; 1: the totals of the last solve_state / solve_adjoint). */
+int glia_rd_create_batch(glia_rd_t** h, const int n[3], int precision, int device, double dt_ctx, int nbatch);
+int glia_rd_batch_size(glia_rd_t* h, int* nbatch);
+int glia_rd_batch_iterations(glia_rd_t* h, int* its_per_member, int accumulated);
+/* wm, gm, csf: ONE member's tissue maps [n0][n1][n2]; k_scale[nbatch], rho_scale[nbatch] (HOST arrays) */
+int glia_rd_set_coefficients_batch(glia_rd_t* h, const void* wm, const void* gm, const void* csf, const double* k_scale,
+                                   double k_gm_wm, double k_glm_wm, double filter_sum, const double* rho_scale,
+                                   double r_gm_wm, double r_glm_wm);
 #define GLIA_IPC_HANDLE_BYTES 64
 /* which: 0 = work arena (after create), 1 = time-history arena (after resize_history) */
 int glia_rd_ipc_export(glia_rd_t* h, int which, void* handle64);

@@ -366,6 +366,57 @@ def case_objective_hessian(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
     return res
 
 
+def case_ensemble_batch(B, n, dtype, nt=2, dt=0.04, members=((0.01, 8.0), (0.05, 4.0), (0.002, 15.0))):
+    """Ensemble handle (glia_rd_create_batch): independent members with their own (kappa, rho) advance through ONE set
+    of kernel launches.  Every member's c(T), alpha(0) and PCG iteration count must be what the oracle gets for that
+    member alone -- members converge at different iterations (a converged member stops, the others continue)."""
+    sh = shape3(n)
+    nb = len(members)
+    P = make_problem(n, dtype)
+    fsum = float(P["filt"].sum(dtype=np.float64))
+    h = RDHandle(n, "f32" if np.dtype(dtype) == np.float32 else "f64", dt_ctx=dt, lib_path=B.lib_path, nbatch=nb,
+                 **({"device": B.device} if hasattr(B, "device") else {}))
+    wm, gm, csf = B.put(P["wm"]), B.put(P["gm"]), B.put(P["csf"])
+    h.set_coefficients_batch(wm, gm, csf, [m[0] for m in members], 0.2, 0.0, fsum, [m[1] for m in members], 0.2, 0.0)
+    h.prec_factor()
+    h.resize_history(nt, dt)
+    c0b = np.ascontiguousarray(np.stack([P["c0"] * (1.0 - 0.1 * i) for i in range(nb)]).astype(dtype))
+    cT = B.empty((nb,) + sh, dtype)
+    tot_s = h.solve_state(B.put(c0b), cT, 0)
+    its_s = h.batch_iterations(True)
+    cTg = B.get(cT)
+    refs = []
+    res = {"cT": [], "p0": [], "its_state": [], "its_adj": []}
+    pTb = np.zeros((nb,) + sh, dtype)
+    for i, (ks, rs) in enumerate(members):
+        k = O.DiffCoef(sh, dtype)
+        k.set_values(ks, 0.2, 0.0, P["wm"], P["gm"], P["csf"], P["filt"])
+        rho = O.reac_coef(rs, 0.2, 0.0, P["wm"], P["gm"], P["csf"])
+        pde = O.PdeOperatorsRD(k, rho, nt, dt, dt_ctx=dt)
+        ref = pde.solve_state(c0b[i], 0)
+        res["cT"].append(rel(cTg[i], ref))
+        res["its_state"].append((its_s[i], pde.ksp_state))
+        pTb[i] = (-(ref - 0.8 * c0b[i])).astype(dtype)
+        refs.append(pde)
+    res["sum_ok"] = (tot_s == sum(its_s))
+    p0 = B.empty((nb,) + sh, dtype)
+    h.solve_adjoint(B.put(pTb), p0, 1, True)
+    its_a = h.batch_iterations(True)
+    p0g = B.get(p0)
+    for i, pde in enumerate(refs):
+        ref = pde.solve_adjoint(pTb[i], 1)
+        res["p0"].append(rel(p0g[i], ref))
+        res["its_adj"].append((its_a[i], pde.ksp_adj))
+    from glia_b200._capi import GliaRdError
+    try:
+        h.grad_kappa_rho(wm, gm, csf)
+        res["guard"] = False
+    except GliaRdError:
+        res["guard"] = True
+    h.close()
+    return res
+
+
 def case_two_snapshot(B, n, dtype, nt=2, dt=0.04, beta=1e-3):
     """two_time_points_ (DerivativeOperatorsRD.cpp:30-34, 149-153, 216-222): the t = 0 mismatch term of the
     objective and its gradient contribution, with a t = 0 observation mask of its own; the Hessian refuses."""

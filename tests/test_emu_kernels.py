@@ -118,3 +118,13 @@ def test_two_snapshot_objective(B):
     assert r["J"] < 1e-10 and r["m0"] < 1e-10 and r["g_c0"] < 1e-9, r
     assert r["hessian_refused"] is True, r
     assert r["J_off"] < 1e-10 and r["m0_off"] == 0.0, r
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_ensemble_batch_handle(B, dtype):
+    r = Cs.case_ensemble_batch(B, 32, dtype, nt=1)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert all(a == b for a, b in r["its_state"]) and all(a == b for a, b in r["its_adj"]), r
+    assert len({a for a, _ in r["its_state"]}) > 1, r     # the members really converge at different iterations
+    assert max(r["cT"]) < tol and max(r["p0"]) < tol, r
+    assert r["sum_ok"] and r["guard"], r

@@ -363,6 +363,19 @@ def test_headline_size_one_time_step_vs_oracle(B):
     assert r["cT"] < 1e-5 and r["p0"] < 1e-5 and r["grad"] < 1e-4, (r["cT"], r["p0"], r["grad"], r["grad_vals"])
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n,nt", [(64, 3), (128, 2)])
+def test_ensemble_batch_handle(B, n, nt, dtype):
+    """BASELINE config 5 in miniature: members with their own (kappa, rho) batched through the kernels' member index;
+    per-member fields and PCG iteration counts equal the oracle's for each member alone."""
+    r = Cs.case_ensemble_batch(B, n, dtype, nt=nt)
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert all(a == b for a, b in r["its_state"]) and all(a == b for a, b in r["its_adj"]), r
+    assert len({a for a, _ in r["its_state"]}) > 1, r
+    assert max(r["cT"]) < tol and max(r["p0"]) < tol, r
+    assert r["sum_ok"] and r["guard"], r
+
+
 def test_wait_stream_orders_a_producer(B):
     """glia_rd_wait_stream: a field produced on another (torch) stream is ordered in front of the library's work
     without a device-wide synchronisation."""
