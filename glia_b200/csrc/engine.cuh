@@ -460,7 +460,7 @@ class Engine : public EngineBase {
   TileX tile_xd() const {
     int sh = 0;
     while ((1 << sh) < n0l) ++sh;
-    return TileX{(long)n[1] * n2c, (long)n2c, (long)n1l * n2c, n2c / SL, n1l, rank * n1l, sh, n0l - 1};
+    return TileX{(long)n[1] * n2c, (long)n2c, (long)n1l * n2c, n2c / SL, ilog2(n2c / SL), n1l, rank * n1l, sh, n0l - 1};
   }
   static dim3 grid_xd(const TileX& g) { return dim3(g.nchunk * g.n_outer); }
   unsigned next_epoch() { return ++epoch; }
@@ -601,7 +601,7 @@ class Engine : public EngineBase {
         // 603 -> 526 us at 512^3, profiles/r2d_zpipe_twldg_ab.txt)
         const long np = lines_z_member().npairs;
         const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());   // of one member
-        int cap = nsm * zpipe_ctas<T, N>() / nb;
+        int cap = nsm * zpipe_ctas<T, N>() / (nb > 2 ? 2 : nb);
         if (cap < 1) cap = 1;
         const int cpm = ngroups < cap ? ngroups : cap;
         LP(tag, kz_deriv2_pipe<T, N, ADD>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), zpipe_smem<T, N>(), zs,
@@ -613,12 +613,15 @@ class Engine : public EngineBase {
       }
     });
   }
+  static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
   RowsS<T> rows_s(const TileS& g, const void* ptr) const {
-    return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, g.nchunk, g.nchunk * g.n_outer, nreal_m / 2};
+    return RowsS<T>{(C*)const_cast<void*>(ptr), g.row_stride, g.outer_stride, ilog2(g.nchunk), nreal_m / 2};
   }
   // persistent S kernels: CTAs per member (ntiles = tiles of ONE member); the grid is cpm x members
+  // (an ensemble's members converge at different iterations and the CTAs of a converged member leave at once: every
+  // member gets CTAs for at least half of the machine, so that the last few unconverged members still fill it)
   template <int N> int cpm_pipe(int ntiles) const {
-    int g = nsm * pipe_ctas<T, N>() / nb;
+    int g = nsm * pipe_ctas<T, N>() / (nb > 2 ? 2 : nb);
     if (g < 1) g = 1;
     return ntiles < g ? ntiles : g;
   }
@@ -647,8 +650,8 @@ class Engine : public EngineBase {
         const PeerGate gate = (G > 1 && gate_pending) ? gate_consumer() : gate_none();
         if constexpr (EPI != EPI_ADD && EPI != EPI_SET) {
           if (acc_extra) {
-            const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, g.nchunk,
-                               g.nchunk * g.n_outer, nreal_m / 2};
+            const RowsS2<T> a2{(C*)acc, (C*)const_cast<T*>(acc_extra), g.row_stride, g.outer_stride, ilog2(g.nchunk),
+                               nreal_m / 2};
             LP(tag, ks_deriv2_pipe<T, N, EPI, RowsS<T>, RowsS<T>, RowsS2<T>, RowsS<T>>, gr, block_s<N>(), pipe_smem<T, N>(),
                st, ntiles, rows_s(g, x), rows_s(g, kfield), a2, rows_s(g, out1), rows_s(g, out2),
                (const C*)tw_for(nline, g), alpha, pp, done, gate, cpm);

@@ -26,7 +26,8 @@ struct TileX {
   long slab_row_stride;    // n1 * n2c       (complex units between x rows inside a slab)
   long slab_outer_stride;  // n2c            (between y)
   long pen_row_stride;     // (n1/G) * n2c   (pencil copy: between x rows)
-  int nchunk;              // n2c / SL
+  int nchunk;              // n2c / SL (a power of two)
+  int cshift;              // log2(nchunk)
   int n_outer;             // n1 / G   tiles per chunk on this rank
   int y0;                  // rank * n1 / G
   int shift, mask;         // x row -> (owner = row >> shift, local row = row & mask)
