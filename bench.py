@@ -773,10 +773,14 @@ def run_slab(a):
                       for r, sl in enumerate(slabs))
             return math.sqrt(num) / max(float(full.double().norm()), 1e-300)
         tol = 1e-5 if a.precision == "f32" else 1e-10
+        # the adjoint starts from p_T = d1 - c(T): a relative difference of c(T) reaches p_T, and with it p(0),
+        # amplified by ||c(T)|| / ||c(T) - d1|| (cancellation) -- the adjoint's own bar is scaled by that factor
+        amp = max(1.0, float(cT1.double().norm()) / max(float((cT1.double() - d11.double()).norm()), 1e-300))
         par = {"what": f"{world}-slab solve vs the 1-GPU solve of the same {a.n}^3 inputs, global relative L2",
                "rel_l2_cT": gl2(slabs_cT, cT1), "rel_l2_p0": gl2(slabs_p0, p01),
-               "its_slab": [int(ks), int(ka)], "its_1gpu": [int(ks1), int(ka1)], "tolerance": tol}
-        par["ok"] = bool(par["rel_l2_cT"] < tol and par["rel_l2_p0"] < tol and par["its_slab"] == par["its_1gpu"])
+               "its_slab": [int(ks), int(ka)], "its_1gpu": [int(ks1), int(ka1)], "tolerance": tol,
+               "terminal_condition_amplification": amp, "tolerance_p0": tol * amp}
+        par["ok"] = bool(par["rel_l2_cT"] < tol and par["rel_l2_p0"] < tol * amp and par["its_slab"] == par["its_1gpu"])
         line["parity"] = par
         line["config"]["parity"] = par
         line["config"]["strong_scaling_base"] = {k: line["strong_scaling_base"][k] for k in
