@@ -79,6 +79,11 @@ struct SyncWarp {
   __device__ __forceinline__ void operator()() const { __syncwarp(); }
   __device__ __forceinline__ void half(int) const { __syncwarp(); }
 };
+// (Measured in round 2 and removed: running the single resident 512-thread CTA of a 512-point S sweep as two column
+// halves of 256 threads with their own named barriers -- lanes along 8 columns, so that a warp touches 64-byte row
+// pieces.  The halves do drift apart, but the half-line global requests cost far more: x.matvec 665 -> 1073 us,
+// y 543 -> 700, ks_c2c.y 169 -> 233 at 512^3 on one box, profiles/r2n_split512_ab.txt.  Same lesson as round 1's
+// 8-column tiles: keep a warp on whole 128-byte rows.)
 
 template <int TPL> struct ZSync { using type = SyncWarp; };
 template <> struct ZSync<64> { using type = SyncCta; };

@@ -128,3 +128,14 @@ def test_ensemble_batch_handle(B, dtype):
     assert len({a for a, _ in r["its_state"]}) > 1, r     # the members really converge at different iterations
     assert max(r["cT"]) < tol and max(r["p0"]) < tol, r
     assert r["sum_ok"] and r["guard"], r
+
+
+def test_s_sweeps_512_point_lines(B):
+    """512-point x lines (three-pass plan, 512-thread CTAs) through the pipelined S kernels: D-apply, operatorA,
+    preconditioner and PCG."""
+    n = (512, 32, 32)
+    e1, e2, budget = Cs.case_apply_D(B, n, np.float32, sinusoidal=False)
+    assert e1 < budget and e2 < budget
+    r = Cs.case_forward_adjoint(B, n, np.float32, nt=1, dt=0.05, with_grad=False)
+    assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], r
+    assert r["cT"] < 1e-5 and r["p0"] < 1e-5, r
