@@ -681,7 +681,15 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
     cp_async_wait<0>();
     sy();  // the r pieces fetched by the other threads of this line pair
   }
+  // Dot products.  Double precision: as the oracle, every product and sum in double.  Single precision: the 2 E
+  // products of ONE thread are summed in float (two FFMA chains per sum), everything across threads, CTAs and ranks
+  // in double.  The all-double form cost this kernel 64 F2F + 119 DADD / DMUL / DFMA per thread next to 412 FP32
+  // instructions (conversion and FP64 pipes at a fraction of the FP32 rate: short-scoreboard 17 % of its stall
+  // samples, profiles/r2l_ncu_source_summary.txt).  A thread's 32-term float sum carries a relative error of a few
+  // 1e-7 with random sign; over the 5e5 threads of a 256^3 field the dot product moves by ~1e-9 relative -- the
+  // reference itself (PETSc VecDot on float Vecs) accumulates everything in float.
   double acc[2] = {0.0, 0.0};
+  [[maybe_unused]] T fa[4] = {(T)0, (T)0, (T)0, (T)0};
   GLIA_UNROLL
   for (int g = 0; g < F::Gp(0); ++g)
     GLIA_UNROLL
@@ -691,12 +699,28 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
       if (z.active) {
         if (zout) { zout[la + pos] = zv.x; zout[lb + pos] = zv.y; }
         if (EPI) {
-          acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
-          if constexpr (EPI == 2) acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
-          else if (r) acc[1] += (double)ld_stream(r + la + pos) * (double)zv.x + (double)ld_stream(r + lb + pos) * (double)zv.y;
+          if constexpr (sizeof(T) == 8) {
+            acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
+            if constexpr (EPI == 2) acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
+            else if (r) acc[1] += (double)ld_stream(r + la + pos) * (double)zv.x + (double)ld_stream(r + lb + pos) * (double)zv.y;
+          } else {
+            fa[0] = zv.x * zv.x + fa[0];
+            fa[1] = zv.y * zv.y + fa[1];
+            if constexpr (EPI == 2) {
+              fa[2] = rst[pos] * zv.x + fa[2];
+              fa[3] = rst[N + pos] * zv.y + fa[3];
+            } else if (r) {
+              fa[2] = ld_stream(r + la + pos) * zv.x + fa[2];
+              fa[3] = ld_stream(r + lb + pos) * zv.y + fa[3];
+            }
+          }
         }
       }
     }
+  if constexpr (sizeof(T) != 8) {
+    acc[0] = (double)fa[0] + (double)fa[1];
+    acc[1] = (double)fa[2] + (double)fa[3];
+  }
   if (EPI) block_reduce_store<2>(acc, partial);
 }
 
