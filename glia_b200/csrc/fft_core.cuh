@@ -113,6 +113,27 @@ __device__ __forceinline__ void prefetch_l1(const V* p) {
 #endif
 }
 
+template <typename V>
+__device__ __forceinline__ void prefetch_l2(const V* p) {
+#if !defined(GLIA_SIMT_EMU)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// One-CTA-per-group Z kernels: the CTA that will run in this CTA's slot `ahead` groups later finds its operand lines
+// in L2 instead of HBM.  `bytes_per_cta` contiguous bytes per CTA starting at base + blockIdx.x * bytes_per_cta; the
+// CTA's threads request one 128-byte line each (32 KB per field in single precision: one instruction per thread).
+#ifndef GLIA_Z_AHEAD
+#define GLIA_Z_AHEAD 444  // 148 SMs x 3 resident CTAs
+#endif
+__device__ __forceinline__ void prefetch_next_cta(const void* base, long bytes_per_cta, long total_bytes) {
+  if (GLIA_Z_AHEAD <= 0) return;
+  const long b0 = ((long)blockIdx.x + GLIA_Z_AHEAD) * bytes_per_cta;
+  for (long i = (long)threadIdx.x * 128; i < bytes_per_cta; i += (long)blockDim.x * 128)
+    if (b0 + i < total_bytes) prefetch_l2(reinterpret_cast<const char*>(base) + b0 + i);
+}
+
 // ---------------------------------------------------------------- plans ----
 // FftPlan<N, V>: V = 0 the default plan; V = 1 the plan of the Z geometry (differs at 512 points only, below)
 template <int N, int V = 0> struct FftPlan;

@@ -647,6 +647,14 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
   const long la = z.pair * 2 * N, lb = la + N;
   const long oa = z.pair * 2 * (N / 2), ob = oa + N / 2;
   AmZ am = z.am();
+  // 512-point lines: the lines of the CTA that follows in this slot go towards L2 now (this kernel's top stall is the
+  // latency of its first loads: long-scoreboard 28 % of the samples, profiles/r2l_ncu_source_summary.txt).  Measured
+  // (profiles/r2t_div_prefetch_ab.txt): kz_c2r.rz 360 -> 332 us at 512^3, but 45.4 -> 49.4 at 256^3, and the same
+  // prefetch in kz_r2c.axpy (which writes r back) tripled that kernel: N = 512 here only.
+  if constexpr (N >= 512) {
+    prefetch_next_cta(shat, (long)zlines<N>() * N * (long)sizeof(cplx<T>), ln.npairs * N * (long)sizeof(cplx<T>));
+    if (EPI && r) prefetch_next_cta(r, (long)zlines<N>() * 2 * N * (long)sizeof(T), ln.npairs * 2 * N * (long)sizeof(T));
+  }
   [[maybe_unused]] T* rst = nullptr;
   if constexpr (EPI == 2) {
     rst = reinterpret_cast<T*>(smraw + sizeof(cplx<T>) * zlines<N>() * zpad<N>()) + (size_t)z.lp * 2 * N;
