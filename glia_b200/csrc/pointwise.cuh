@@ -176,6 +176,32 @@ __global__ void k_cg_update(long n, const T* xin, T* x, T* p, const T* __restric
   const T a = (T)scal[S_A], b = (T)scal[S_B];
   const int done = iscal[I_DONE];
   const long stride = (long)gridDim.x * blockDim.x;
+  // 16-byte accesses where the member's fields allow it (n a multiple of the vector width, 16-byte aligned bases)
+  constexpr int V = 16 / (int)sizeof(T);
+  struct alignas(16) Vec { T e[V]; };
+  const bool vec = (n % V == 0) && ((((size_t)xin | (size_t)x | (size_t)p | (size_t)z) & 15) == 0);
+  if (vec) {
+    const long nv = n / V;
+    const Vec* xin4 = reinterpret_cast<const Vec*>(xin);
+    const Vec* z4 = reinterpret_cast<const Vec*>(z);
+    Vec* x4 = reinterpret_cast<Vec*>(x);
+    Vec* p4 = reinterpret_cast<Vec*>(p);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const Vec pv = p4[i], xv = xin4[i];
+      Vec xo;
+      GLIA_UNROLL
+      for (int k = 0; k < V; ++k) xo.e[k] = xv.e[k] + a * pv.e[k];
+      x4[i] = xo;
+      if (!done) {
+        const Vec zv = z4[i];
+        Vec po;
+        GLIA_UNROLL
+        for (int k = 0; k < V; ++k) po.e[k] = zv.e[k] + b * pv.e[k];
+        p4[i] = po;
+      }
+    }
+    return;
+  }
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const T pv = p[i];
     x[i] = xin[i] + a * pv;
