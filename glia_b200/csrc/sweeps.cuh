@@ -689,7 +689,7 @@ kz_c2r(LinesZ ln, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict
     cp_async_wait<0>();
     sy();  // the r pieces fetched by the other threads of this line pair
   }
-  // Dot products.  Double precision: as the oracle, every product and sum in double.  Single precision: the 2 E
+  // Dot products.  Double precision: every product and sum in double.  Single precision: the 2 E
   // products of ONE thread are summed in float (two FFMA chains per sum), everything across threads, CTAs and ranks
   // in double.  The all-double form cost this kernel 64 F2F + 119 DADD / DMUL / DFMA per thread next to 412 FP32
   // instructions (conversion and FP64 pipes at a fraction of the FP32 rate: short-scoreboard 17 % of its stall
