@@ -1,8 +1,14 @@
-// simt_emu.h -- TEST INFRASTRUCTURE ONLY.  A thread-per-CUDA-thread SIMT emulator that lets
-// g++ compile glia_b200/csrc/*.cu(h) (with -DGLIA_SIMT_EMU -Itests/emu) so that kernel index
-// logic and the host-side PCG / time-stepping drivers can be exercised on a machine with no
-// GPU.  Every CUDA thread of a CTA runs as an OS thread with real barriers; CTAs run one
-// after another.  It is never loaded by the glia_b200 package.
+// simt_emu.h -- TEST INFRASTRUCTURE ONLY.  A SIMT emulator that lets g++ compile
+// glia_b200/csrc/*.cu(h) (with -DGLIA_SIMT_EMU -Itests/emu) so that kernel index logic and the
+// host-side PCG / time-stepping drivers can be exercised on a machine with no GPU.  It is never
+// loaded by the glia_b200 package.
+//
+// Every CUDA thread of a CTA runs as a FIBER (its own 64 KB stack, cooperative switch at barriers) on
+// the OS thread that executes the CTA; a launch hands its CTAs, in index order, to a small pool of OS
+// threads.  __syncthreads / __syncwarp / named half barriers are generation counters: a fiber that
+// arrives early yields to the next fiber of its CTA.  (The first version ran one OS thread per CUDA
+// thread with std::barrier: correct, but a 512-thread CTA spent its time in futex calls -- the CPU
+// suite took 10 minutes.)  On targets other than x86-64 the OS-thread form below is used.
 #pragma once
 #include <atomic>
 #include <fcntl.h>
@@ -14,6 +20,8 @@
 #endif
 #include <barrier>
 #include <chrono>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <string>
@@ -26,7 +34,8 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+// "shared" statics: one copy per OS thread = per CTA in flight (CTAs of a launch run on several OS threads)
+#define __shared__ static thread_local
 #define GLIA_UNROLL
 
 struct dim3 {
@@ -35,6 +44,179 @@ struct dim3 {
 };
 typedef int cudaStream_t;
 
+#if defined(__x86_64__) && !defined(GLIA_EMU_OS_THREADS)
+// =============================================================== fibers ====
+namespace emu {
+struct Bar {  // generation barrier among fibers of one OS thread: no atomics needed
+  int n = 1, count = 0;
+  unsigned gen = 0;
+};
+struct Ctx {
+  dim3 tid, bid, bdim, gdim;
+  unsigned char* smem = nullptr;
+  Bar* cta_bar = nullptr;
+  Bar* half_bar[2] = {nullptr, nullptr};  // bar.sync 1 / 2 over the lower / upper half of the CTA's threads
+  Bar* warp_bar = nullptr;
+  unsigned char* warp_slots = nullptr;  // 32 x 16 bytes scratch for shuffles
+  int lane = 0;
+  // fiber state
+  void* sp = nullptr;
+  bool finished = false;
+};
+struct Worker {  // one per OS thread that executes CTAs
+  std::vector<Ctx> fib;
+  std::vector<void*> stacks;  // reused across launches
+  int nthr = 0, cur = 0, live = 0;
+  void* main_sp = nullptr;
+  const std::function<void()>* body = nullptr;
+  ~Worker() {
+    for (void* st : stacks) munmap(st, kStack);
+  }
+  static constexpr size_t kStack = 64 * 1024;
+};
+inline thread_local Worker worker;
+inline thread_local Ctx* cur = nullptr;
+
+// save the callee-saved registers on the current stack, publish its stack pointer, continue on `to`
+__attribute__((naked, noinline)) static void fiber_switch(void** /*from_sp*/, void* /*to_sp*/) {
+  asm volatile(
+      "pushq %rbp\n pushq %rbx\n pushq %r12\n pushq %r13\n pushq %r14\n pushq %r15\n"
+      "movq %rsp, (%rdi)\n"
+      "movq %rsi, %rsp\n"
+      "popq %r15\n popq %r14\n popq %r13\n popq %r12\n popq %rbx\n popq %rbp\n"
+      "ret\n");
+}
+inline void switch_to(int j) {
+  Worker& w = worker;
+  Ctx* from = &w.fib[w.cur];
+  w.cur = j;
+  cur = &w.fib[j];
+  fiber_switch(&from->sp, w.fib[j].sp);
+}
+// run somebody else of this CTA; returns when this fiber is resumed
+inline void yield() {
+  Worker& w = worker;
+  int j = w.cur;
+  for (int k = 1; k < w.nthr; ++k) {
+    if (++j == w.nthr) j = 0;
+    if (!w.fib[j].finished) { switch_to(j); return; }
+  }
+}
+inline void bar_wait(Bar* b) {
+  const unsigned g = b->gen;
+  if (++b->count == b->n) {
+    b->count = 0;
+    ++b->gen;
+  } else {
+    while (b->gen == g) yield();
+  }
+}
+[[noreturn]] static void fiber_main() {
+  Worker& w = worker;
+  (*w.body)();
+  Ctx* me = &w.fib[w.cur];
+  me->finished = true;
+  if (--w.live == 0) {
+    cur = nullptr;
+    fiber_switch(&me->sp, w.main_sp);
+  } else {
+    int j = w.cur;
+    for (;;) {
+      if (++j == w.nthr) j = 0;
+      if (!w.fib[j].finished) break;
+    }
+    w.cur = j;
+    cur = &w.fib[j];
+    fiber_switch(&me->sp, w.fib[j].sp);
+  }
+  std::abort();  // a finished fiber is never resumed
+}
+
+template <class F>
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
+  const int nthr = (int)(block.x * block.y * block.z);
+  const int nwarp = (nthr + 31) / 32;
+  const long ncta = (long)grid.x * grid.y * grid.z;
+  const std::function<void()> body = f;
+  std::atomic<long> next{0};
+  auto run = [&]() {
+    Worker& w = worker;
+    w.nthr = nthr;
+    w.body = &body;
+    if ((int)w.fib.size() < nthr) w.fib.resize(nthr);
+    while ((int)w.stacks.size() < nthr) {
+      void* st = mmap(nullptr, Worker::kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+      if (st == MAP_FAILED) std::abort();
+      w.stacks.push_back(st);
+    }
+    std::vector<unsigned char> smem(smem_bytes + 64);
+    Bar cta_bar, half_lo, half_hi;
+    std::vector<Bar> wbars(nwarp);
+    std::vector<unsigned char> wslots((size_t)nwarp * 32 * 16);
+    for (;;) {
+      const long c = next.fetch_add(1);  // CTAs start in index order
+      if (c >= ncta) break;
+      cta_bar = Bar{nthr};
+      half_lo = Bar{nthr / 2 > 0 ? nthr / 2 : 1};
+      half_hi = Bar{nthr - nthr / 2 > 0 ? nthr - nthr / 2 : 1};
+      for (int wi = 0; wi < nwarp; ++wi) wbars[wi] = Bar{(wi == nwarp - 1) ? nthr - 32 * wi : 32};
+      const dim3 bid((unsigned)(c % grid.x), (unsigned)((c / grid.x) % grid.y), (unsigned)(c / ((long)grid.x * grid.y)));
+      for (int i = 0; i < nthr; ++i) {
+        Ctx& x = w.fib[i];
+        x.bdim = block;
+        x.gdim = grid;
+        x.bid = bid;
+        x.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
+        x.smem = smem.data();
+        x.cta_bar = &cta_bar;
+        x.half_bar[0] = &half_lo;
+        x.half_bar[1] = &half_hi;
+        x.warp_bar = &wbars[i / 32];
+        x.warp_slots = wslots.data() + (size_t)(i / 32) * 32 * 16;
+        x.lane = i % 32;
+        x.finished = false;
+        // initial frame: six zeroed callee-saved registers, the entry point, one slot so that the entry sees the
+        // stack as after a call (rsp = 16 n + 8)
+        void** top = reinterpret_cast<void**>(static_cast<unsigned char*>(w.stacks[i]) + Worker::kStack);
+        top[-1] = nullptr;
+        top[-2] = reinterpret_cast<void*>(&fiber_main);
+        for (int k = 3; k <= 8; ++k) top[-k] = nullptr;
+        x.sp = top - 8;
+      }
+      w.live = nthr;
+      w.cur = 0;
+      cur = &w.fib[0];
+      fiber_switch(&w.main_sp, w.fib[0].sp);  // returns when the last fiber of the CTA has finished
+    }
+  };
+  unsigned nworker = std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("GLIA_EMU_WORKERS")) nworker = (unsigned)std::atoi(e);
+  if (nworker < 1) nworker = 1;
+  if (nworker > 8) nworker = 8;
+  if ((long)nworker > ncta) nworker = (unsigned)ncta;
+  if (nworker <= 1) {
+    run();
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < nworker; ++i) th.emplace_back(run);
+    for (auto& t : th) t.join();
+  }
+}
+}  // namespace emu
+
+#define threadIdx (emu::cur->tid)
+#define blockIdx (emu::cur->bid)
+#define blockDim (emu::cur->bdim)
+#define gridDim (emu::cur->gdim)
+#define GLIA_EMU_CTX (*emu::cur)
+
+inline void __syncthreads() { emu::bar_wait(emu::cur->cta_bar); }
+inline void emu_half_barrier(int h) { emu::bar_wait(emu::cur->half_bar[h]); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::bar_wait(emu::cur->warp_bar); }
+inline void emu_warp_barrier() { emu::bar_wait(emu::cur->warp_bar); }
+
+#else
+// ============================================================ OS threads ====
 namespace emu {
 struct Ctx {
   dim3 tid, bid, bdim, gdim;
@@ -88,32 +270,37 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
 }
 }  // namespace emu
 
+#undef __shared__
+#define __shared__ static
 #define threadIdx (emu::ctx.tid)
 #define blockIdx (emu::ctx.bid)
 #define blockDim (emu::ctx.bdim)
 #define gridDim (emu::ctx.gdim)
+#define GLIA_EMU_CTX (emu::ctx)
 
 inline void __syncthreads() { emu::ctx.cta_bar->arrive_and_wait(); }
 inline void emu_half_barrier(int h) { emu::ctx.half_bar[h]->arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.warp_bar->arrive_and_wait(); }
+inline void emu_warp_barrier() { emu::ctx.warp_bar->arrive_and_wait(); }
+#endif
 
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) {
   static_assert(sizeof(T) <= 16, "shuffle payload");
-  auto& c = emu::ctx;
+  auto& c = GLIA_EMU_CTX;
   std::memcpy(c.warp_slots + 16 * c.lane, &v, sizeof(T));
-  c.warp_bar->arrive_and_wait();
+  emu_warp_barrier();
   T r;
   std::memcpy(&r, c.warp_slots + 16 * (src & 31), sizeof(T));
-  c.warp_bar->arrive_and_wait();
+  emu_warp_barrier();
   return r;
 }
 template <class T>
-inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, emu::ctx.lane ^ mask); }
+inline T __shfl_xor_sync(unsigned m, T v, int mask) { return __shfl_sync(m, v, GLIA_EMU_CTX.lane ^ mask); }
 template <class T>
 inline T __shfl_down_sync(unsigned m, T v, int d) {
-  int s = emu::ctx.lane + d;
-  return __shfl_sync(m, v, s > 31 ? emu::ctx.lane : s);
+  int s = GLIA_EMU_CTX.lane + d;
+  return __shfl_sync(m, v, s > 31 ? GLIA_EMU_CTX.lane : s);
 }
 
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
@@ -122,7 +309,7 @@ inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
-#define GLIA_DYN_SMEM(name) unsigned char* name = emu::ctx.smem
+#define GLIA_DYN_SMEM(name) unsigned char* name = GLIA_EMU_CTX.smem
 
 namespace simt {
 template <class... KA, class... A>

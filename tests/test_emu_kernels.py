@@ -1,5 +1,5 @@
 """CPU tests of the product kernel sources and host drivers through the test-only SIMT
-emulator build (tests/emu): same C ABI, same code, OS threads instead of CUDA threads.
+emulator build (tests/emu): same C ABI, same code, fibers instead of CUDA threads.
 Small grids only; the parity tests proper are the gpu ones."""
 import numpy as np
 import pytest
