@@ -814,10 +814,22 @@ class Engine : public EngineBase {
     });
     GLIA_DISPATCH_N(n[2], {
       nblk = bpm_z<N>();   // partial sums per member
-      if (zout && want_rz)
-        LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
-           lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, bpm_z<N>());
-      else
+      if (zout && want_rz) {
+        if constexpr (c2rpipe_fits<T, N>()) {
+          // persistent warp-private pipelined form (sweeps_zpipe.cuh)
+          const long np = lines_z_member().npairs;
+          const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());   // of one member
+          int cap = nsm * 2 / (nb > 2 ? 2 : nb);
+          if (cap < 1) cap = 1;
+          const int cpm = ngroups < cap ? ngroups : cap;
+          nblk = cpm;
+          LP("kz_c2r.rz", kz_c2r_pipe<T, N>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), c2rpipe_smem<T, N>(), st,
+             lines_z_member(), ngroups, (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, cpm);
+        } else {
+          LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
+             lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, bpm_z<N>());
+        }
+      } else
         LP(zout ? "kz_c2r" : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(),
            (const C*)shat, zout, (const T*)nullptr, pp, (const C*)tw[2], done, bpm_z<N>());
     });

@@ -129,4 +129,130 @@ kz_deriv2_pipe(LinesZ ln, int ngroups, const T* __restrict__ x, const T* __restr
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// kz_c2r_pipe: the preconditioner's last sweep (packed half spectra -> two real z lines, z = M^-1 r, partial sums
+// {<z,z>, <r,z>}) in the same persistent, warp-private form.  The one-group-per-CTA kz_c2r ran at 35 % issue
+// activity and 47 % of the DRAM rate with 36 % of the warp slots filled (ncu, profiles/r2w_ncu_full_summary.csv):
+// every CTA starts with the full latency of its spectrum loads.  Here the NEXT group's spectrum lines ride into the
+// pair's stage as soon as the current group has been unpacked out of it, and the next group's r lines as soon as
+// the epilogue has read the current ones; both buffers are single:
+//   smem per line pair = spectrum stage (N complex) | r stage (2N reals) | exchange (zpad complex)
+//   cp.async groups in flight, in commit order: [spectrum(g), r(g)] at the top of group g, [r(g), spectrum(g+)] after
+//   the unpack -- wait_group<1> serves both waits.
+template <typename T, int N>
+__host__ __device__ constexpr size_t c2rpipe_pair_bytes() {
+  return (size_t)N * sizeof(cplx<T>) + (size_t)(2 * N) * sizeof(T) + (size_t)zpad<N>() * sizeof(cplx<T>);
+}
+template <typename T, int N>
+__host__ __device__ constexpr size_t c2rpipe_smem() { return zlines<N>() * c2rpipe_pair_bytes<T, N>(); }
+template <typename T, int N>
+__host__ __device__ constexpr bool c2rpipe_fits() {
+  return (N / FftPlan<N>::E) <= 32 && c2rpipe_smem<T, N>() <= 110 * 1024;  // two CTAs per SM
+}
+template <typename T, int N>
+__global__ void __launch_bounds__(zthreads<N>(), 2)
+kz_c2r_pipe(LinesZ ln, int ngroups, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict__ r, double* partial,
+            const cplx<T>* __restrict__ twt, const int* __restrict__ done, int cpm) {
+  // ln.npairs, ngroups: line pairs / groups of zlines<N>() pairs of ONE ensemble member; cpm = CTAs per member
+  const int member = blockIdx.x / cpm, cl = blockIdx.x % cpm;
+  done = member_done(done, member);
+  GLIA_PDL_ENTRY_EARLY(done);
+  using F = LineFft<T, N, zplan<N>()>;
+  constexpr int E = F::E, TPL = F::TPL, LPC = zlines<N>();
+  static_assert(TPL <= 32, "a line pair must live inside one warp");
+  GLIA_DYN_SMEM(smraw);
+  const int t = threadIdx.x % TPL, lp = threadIdx.x / TPL;
+  unsigned char* mine = smraw + (size_t)lp * c2rpipe_pair_bytes<T, N>();
+  cplx<T>* sst = reinterpret_cast<cplx<T>*>(mine);                             // [0, N/2): line a, [N/2, N): line b
+  T* rst = reinterpret_cast<T*>(mine + (size_t)N * sizeof(cplx<T>));           // [0, N): line a, [N, 2N): line b
+  cplx<T>* sm = reinterpret_cast<cplx<T>*>(mine + (size_t)N * sizeof(cplx<T>) + (size_t)(2 * N) * sizeof(T));
+  typename F::Tw tw;
+  F::load_twiddles(tw, twt, t);
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
+  SyncWarp sy;
+  const AmZ am{0};
+  constexpr int CH = (N * (int)sizeof(cplx<T>)) / 16;  // 16-byte chunks of one pair's spectra = of its two r lines
+  static_assert(CH % TPL == 0, "chunks per thread");
+  const long pair0 = (long)member * ln.npairs;
+  auto pair_of = [&](int group) -> long {
+    long p = (long)group * LPC + lp;
+    return pair0 + (p < ln.npairs ? p : ln.npairs - 1);  // ragged tail: re-do the last pair, stores predicated
+  };
+  auto fetch = [&](void* stage, const void* line0) {
+    GLIA_UNROLL
+    for (int i = 0; i < CH / TPL; ++i) {
+      const int c = t + i * TPL;
+      cp_async16(reinterpret_cast<char*>(stage) + 16 * c, reinterpret_cast<const char*>(line0) + 16 * c);
+    }
+  };
+  double acc[2] = {0.0, 0.0};
+  int group = cl;
+  if (group < ngroups) fetch(sst, shat + pair_of(group) * N);
+  cp_async_commit();
+  if (group < ngroups) fetch(rst, r + pair_of(group) * 2 * N);
+  cp_async_commit();
+  for (; group < ngroups; group += cpm) {
+    const long pair = pair_of(group);
+    const bool active = (long)group * LPC + lp < ln.npairs;
+    const long la = pair * 2 * N, lb = la + N;
+    cp_async_wait<1>();  // this group's spectra (its r lines may still be in flight)
+    sy();
+    // untangle the two Hermitian half spectra into one complex line, placed where the inverse's first pass reads
+    GLIA_UNROLL
+    for (int j = 0; j < E / 2; ++j) {
+      const int k = t + TPL * j;
+      const cplx<T> A = sst[k], B = sst[N / 2 + k];
+      if (k == 0) {
+        sm[am(F::loc_of_freq(0))] = {A.x, B.x};
+        sm[am(F::loc_of_freq(N / 2))] = {A.y, B.y};
+      } else {
+        sm[am(F::loc_of_freq(k))] = {A.x - B.y, A.y + B.x};
+        sm[am(F::loc_of_freq(N - k))] = {A.x + B.y, B.x - A.y};
+      }
+    }
+    sy();  // the pair's spectrum stage has been read by all of its lanes: refill it with the next group's
+    const int next = group + cpm;
+    if (next < ngroups) fetch(sst, shat + pair_of(next) * N);
+    cp_async_commit();
+    cplx<T> v[E];
+    GLIA_UNROLL
+    for (int g = 0; g < F::Gp(F::P - 1); ++g)
+      GLIA_UNROLL
+      for (int cc = 0; cc < F::RL; ++cc) v[g * F::RL + cc] = sm[am(F::template loc<F::P - 1>(t, g, cc))];
+    F::inverse(v, tw, sm, am, sy, t);
+    cp_async_wait<1>();  // this group's r lines (the next group's spectra stay in flight)
+    sy();
+    [[maybe_unused]] T fa[4] = {(T)0, (T)0, (T)0, (T)0};
+    GLIA_UNROLL
+    for (int g = 0; g < F::Gp(0); ++g)
+      GLIA_UNROLL
+      for (int a = 0; a < F::R(0); ++a) {
+        const int pos = F::template loc<0>(t, g, a);
+        const cplx<T> zv = v[g * F::R(0) + a];
+        if (active) {
+          zout[la + pos] = zv.x;
+          zout[lb + pos] = zv.y;
+          if constexpr (sizeof(T) == 8) {
+            acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
+            acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
+          } else {  // per-thread float partials (see kz_c2r, sweeps.cuh)
+            fa[0] = zv.x * zv.x + fa[0];
+            fa[1] = zv.y * zv.y + fa[1];
+            fa[2] = rst[pos] * zv.x + fa[2];
+            fa[3] = rst[N + pos] * zv.y + fa[3];
+          }
+        }
+      }
+    if constexpr (sizeof(T) != 8) {
+      acc[0] += (double)fa[0] + (double)fa[1];
+      acc[1] += (double)fa[2] + (double)fa[3];
+    }
+    sy();  // the pair's r stage has been read: the next group's lines may land
+    if (next < ngroups) fetch(rst, r + pair_of(next) * 2 * N);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  block_reduce_store<2>(acc, partial);
+}
+
 }  // namespace glia
