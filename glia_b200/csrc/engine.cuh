@@ -577,6 +577,18 @@ class Engine : public EngineBase {
     const long np = lines_z_member().npairs;
     return (int)((np + zlines<N>() - 1) / zlines<N>());
   }
+  // persistent Z kernels with two resident CTAs per SM (kz_r2c_pipe, kz_c2r_pipe): groups of zlines<N>() line pairs
+  // of one member, CTAs per member
+  template <int N> int zgroups() const {
+    const long np = lines_z_member().npairs;
+    return (int)((np + zlines<N>() - 1) / zlines<N>());
+  }
+  template <int N> int cpm_zpipe2() const {
+    int cap = nsm * 2 / (nb > 2 ? 2 : nb);
+    if (cap < 1) cap = 1;
+    const int g = zgroups<N>();
+    return g < cap ? g : cap;
+  }
   template <int N> dim3 grid_z() const {
     if (nb > 1 && lines_z_member().npairs % zlines<N>() != 0) throw EngineError{"ensemble handle: grid too small for the z sweeps"};
     return dim3((unsigned)(bpm_z<N>() * nb));
@@ -740,15 +752,28 @@ class Engine : public EngineBase {
   int pc_apply(T* rin, const T* wv, T* zout, bool want_rz, double* pp, const int* done) {
     const TileS ty = tile_y(), tx = tile_x();
     int nblk = 0;
-    if (wv) {
-      GLIA_DISPATCH_N(n[2], LP("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                         lines_z(), rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done,
-                                         bpm_z<N>()));
-    } else {
-      GLIA_DISPATCH_N(n[2], LP("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st,
-                                         lines_z(), rin, (const T*)nullptr, (const double*)nullptr, shat,
-                                         (const C*)tw[2], done, bpm_z<N>()));
-    }
+    GLIA_DISPATCH_N(n[2], {
+      if constexpr (r2cpipe_fits<T, N>()) {  // persistent warp-private pipelined form (sweeps_zpipe.cuh)
+        const int ngroups = zgroups<N>(), cpm = cpm_zpipe2<N>();
+        // (the r <- r - a w form at 512-point lines keeps the one-group-per-CTA kernel: it runs at the copy rate there,
+        // 328 us against 350 us pipelined, profiles/r3a_r2cpipe_ab.txt; an ensemble handle needs the member-aware form)
+        if (wv && (N < 512 || nb > 1))
+          LP("kz_r2c.axpy", kz_r2c_pipe<T, N, 1>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), r2cpipe_smem<T, N>(), st,
+             lines_z_member(), ngroups, rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done, cpm);
+        else if (wv)
+          LP("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), rin, wv,
+             (const double*)(scal + S_A), shat, (const C*)tw[2], done, bpm_z<N>());
+        else
+          LP("kz_r2c", kz_r2c_pipe<T, N, 0>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), r2cpipe_smem<T, N>(), st,
+             lines_z_member(), ngroups, rin, (const T*)nullptr, (const double*)nullptr, shat, (const C*)tw[2], done, cpm);
+      } else if (wv) {
+        LP("kz_r2c.axpy", kz_r2c<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), rin, wv,
+           (const double*)(scal + S_A), shat, (const C*)tw[2], done, bpm_z<N>());
+      } else {
+        LP("kz_r2c", kz_r2c<T, N, 0>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(), rin,
+           (const T*)nullptr, (const double*)nullptr, shat, (const C*)tw[2], done, bpm_z<N>());
+      }
+    });
     GLIA_DISPATCH_N(n[1], {
       if constexpr (pipe_fits<T, N>()) {
         const int ntiles = ty.nchunk * ty.n_outer;
@@ -814,24 +839,23 @@ class Engine : public EngineBase {
     });
     GLIA_DISPATCH_N(n[2], {
       nblk = bpm_z<N>();   // partial sums per member
-      if (zout && want_rz) {
-        if constexpr (c2rpipe_fits<T, N>()) {
-          // persistent warp-private pipelined form (sweeps_zpipe.cuh)
-          const long np = lines_z_member().npairs;
-          const int ngroups = (int)((np + zlines<N>() - 1) / zlines<N>());   // of one member
-          int cap = nsm * 2 / (nb > 2 ? 2 : nb);
-          if (cap < 1) cap = 1;
-          const int cpm = ngroups < cap ? ngroups : cap;
-          nblk = cpm;
-          LP("kz_c2r.rz", kz_c2r_pipe<T, N>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), c2rpipe_smem<T, N>(), st,
+      if constexpr (c2rpipe_fits<T, N>()) {  // persistent warp-private pipelined form (sweeps_zpipe.cuh)
+        const int ngroups = zgroups<N>(), cpm = cpm_zpipe2<N>();
+        nblk = cpm;
+        if (zout && want_rz)
+          LP("kz_c2r.rz", kz_c2r_pipe<T, N, 2>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), c2rpipe_smem<T, N>(), st,
              lines_z_member(), ngroups, (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, cpm);
-        } else {
-          LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
-             lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, bpm_z<N>());
-        }
-      } else
+        else
+          LP(zout ? "kz_c2r" : "kz_c2r.norm", kz_c2r_pipe<T, N, 1>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()),
+             c2rpipe_smem<T, N>(), st, lines_z_member(), ngroups, (const C*)shat, zout, (const T*)nullptr, pp,
+             (const C*)tw[2], done, cpm);
+      } else if (zout && want_rz) {
+        LP("kz_c2r.rz", kz_c2r<T, N, 2>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>() + smem_z_rstage<N, T>(), st,
+           lines_z(), (const C*)shat, zout, (const T*)rin, pp, (const C*)tw[2], done, bpm_z<N>());
+      } else {
         LP(zout ? "kz_c2r" : "kz_c2r.norm", kz_c2r<T, N, 1>, grid_z<N>(), dim3(zthreads<N>()), smem_z<N>(), st, lines_z(),
            (const C*)shat, zout, (const T*)nullptr, pp, (const C*)tw[2], done, bpm_z<N>());
+      }
     });
     return nblk;
   }

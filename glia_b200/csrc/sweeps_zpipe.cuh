@@ -149,7 +149,8 @@ template <typename T, int N>
 __host__ __device__ constexpr bool c2rpipe_fits() {
   return (N / FftPlan<N>::E) <= 32 && c2rpipe_smem<T, N>() <= 110 * 1024;  // two CTAs per SM
 }
-template <typename T, int N>
+//   EPI 2: <z,z>, <r,z> (z and r given); EPI 1: <z,z> only (r unused; zout may be null: rnorm0 = ||M^-1 b||)
+template <typename T, int N, int EPI>
 __global__ void __launch_bounds__(zthreads<N>(), 2)
 kz_c2r_pipe(LinesZ ln, int ngroups, const cplx<T>* __restrict__ shat, T* zout, const T* __restrict__ r, double* partial,
             const cplx<T>* __restrict__ twt, const int* __restrict__ done, int cpm) {
@@ -189,7 +190,7 @@ kz_c2r_pipe(LinesZ ln, int ngroups, const cplx<T>* __restrict__ shat, T* zout, c
   int group = cl;
   if (group < ngroups) fetch(sst, shat + pair_of(group) * N);
   cp_async_commit();
-  if (group < ngroups) fetch(rst, r + pair_of(group) * 2 * N);
+  if (EPI == 2 && group < ngroups) fetch(rst, r + pair_of(group) * 2 * N);
   cp_async_commit();
   for (; group < ngroups; group += cpm) {
     const long pair = pair_of(group);
@@ -230,16 +231,20 @@ kz_c2r_pipe(LinesZ ln, int ngroups, const cplx<T>* __restrict__ shat, T* zout, c
         const int pos = F::template loc<0>(t, g, a);
         const cplx<T> zv = v[g * F::R(0) + a];
         if (active) {
-          zout[la + pos] = zv.x;
-          zout[lb + pos] = zv.y;
+          if (EPI == 2 || zout) {
+            zout[la + pos] = zv.x;
+            zout[lb + pos] = zv.y;
+          }
           if constexpr (sizeof(T) == 8) {
             acc[0] += (double)zv.x * (double)zv.x + (double)zv.y * (double)zv.y;
-            acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
+            if constexpr (EPI == 2) acc[1] += (double)rst[pos] * (double)zv.x + (double)rst[N + pos] * (double)zv.y;
           } else {  // per-thread float partials (see kz_c2r, sweeps.cuh)
             fa[0] = zv.x * zv.x + fa[0];
             fa[1] = zv.y * zv.y + fa[1];
-            fa[2] = rst[pos] * zv.x + fa[2];
-            fa[3] = rst[N + pos] * zv.y + fa[3];
+            if constexpr (EPI == 2) {
+              fa[2] = rst[pos] * zv.x + fa[2];
+              fa[3] = rst[N + pos] * zv.y + fa[3];
+            }
           }
         }
       }
@@ -248,11 +253,134 @@ kz_c2r_pipe(LinesZ ln, int ngroups, const cplx<T>* __restrict__ shat, T* zout, c
       acc[1] += (double)fa[2] + (double)fa[3];
     }
     sy();  // the pair's r stage has been read: the next group's lines may land
-    if (next < ngroups) fetch(rst, r + pair_of(next) * 2 * N);
+    if (EPI == 2 && next < ngroups) fetch(rst, r + pair_of(next) * 2 * N);
     cp_async_commit();
   }
   cp_async_wait<0>();
   block_reduce_store<2>(acc, partial);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kz_r2c_pipe: the preconditioner's first sweep (two real z lines -> two packed half spectra, optional PCG prologue
+// r <- r - a w with r written back) in the same form: the pair's r (and w) lines are read out of their stage into
+// registers at the top of a group and the next group's lines ride in behind them while this group is transformed.
+//   smem per line pair = r stage (2N reals) | w stage (2N reals) | exchange (zpad complex)
+template <typename T, int N>
+__host__ __device__ constexpr size_t r2cpipe_pair_bytes() {
+  return 2 * (size_t)(2 * N) * sizeof(T) + (size_t)zpad<N>() * sizeof(cplx<T>);
+}
+template <typename T, int N>
+__host__ __device__ constexpr size_t r2cpipe_smem() { return zlines<N>() * r2cpipe_pair_bytes<T, N>(); }
+template <typename T, int N>
+__host__ __device__ constexpr bool r2cpipe_fits() {
+  return (N / FftPlan<N>::E) <= 32 && r2cpipe_smem<T, N>() <= 110 * 1024;  // two CTAs per SM
+}
+template <typename T, int N, int PRO>
+__global__ void __launch_bounds__(zthreads<N>(), 2)
+kz_r2c_pipe(LinesZ ln, int ngroups, T* r, const T* __restrict__ w, const double* __restrict__ scal_a, cplx<T>* shat,
+            const cplx<T>* __restrict__ twt, const int* __restrict__ done, int cpm) {
+  const int member = blockIdx.x / cpm, cl = blockIdx.x % cpm;
+  done = member_done(done, member);
+  GLIA_PDL_ENTRY_EARLY(done);
+  using F = LineFft<T, N, zplan<N>()>;
+  constexpr int E = F::E, TPL = F::TPL, LPC = zlines<N>();
+  static_assert(TPL <= 32, "a line pair must live inside one warp");
+  GLIA_DYN_SMEM(smraw);
+  const int t = threadIdx.x % TPL, lp = threadIdx.x / TPL;
+  unsigned char* mine = smraw + (size_t)lp * r2cpipe_pair_bytes<T, N>();
+  T* rst = reinterpret_cast<T*>(mine);
+  T* wst = rst + 2 * N;
+  cplx<T>* sm = reinterpret_cast<cplx<T>*>(mine + 2 * (size_t)(2 * N) * sizeof(T));
+  typename F::Tw tw;
+  F::load_twiddles(tw, twt, t);
+  GLIA_PDL_ENTRY_LATE(done);  // everything above is independent of earlier kernels
+  SyncWarp sy;
+  const AmZ am{0};
+  constexpr int CH = (2 * N * (int)sizeof(T)) / 16;  // 16-byte chunks of one pair's two lines
+  static_assert(CH % TPL == 0, "chunks per thread");
+  const long pair0 = (long)member * ln.npairs;
+  auto pair_of = [&](int group) -> long {
+    long p = (long)group * LPC + lp;
+    return pair0 + (p < ln.npairs ? p : ln.npairs - 1);
+  };
+  auto fetch = [&](void* stage, const void* line0) {
+    GLIA_UNROLL
+    for (int i = 0; i < CH / TPL; ++i) {
+      const int c = t + i * TPL;
+      cp_async16(reinterpret_cast<char*>(stage) + 16 * c, reinterpret_cast<const char*>(line0) + 16 * c);
+    }
+  };
+  T aa = (T)0;
+  if (PRO) aa = (T)(scal_a[(size_t)member * SCAL_STRIDE]);
+  int group = cl;
+  if (group < ngroups) {
+    fetch(rst, r + pair_of(group) * 2 * N);
+    if (PRO) fetch(wst, w + pair_of(group) * 2 * N);
+  }
+  cp_async_commit();
+  for (; group < ngroups; group += cpm) {
+    const long pair = pair_of(group);
+    const bool active = (long)group * LPC + lp < ln.npairs;
+    const long la = pair * 2 * N, lb = la + N;
+    cp_async_wait<0>();
+    sy();
+    cplx<T> v[E];
+    GLIA_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+      cplx<T> rv = {rst[pos], rst[N + pos]};
+      if (PRO) {
+        rv.x = rv.x - aa * wst[pos];
+        rv.y = rv.y - aa * wst[N + pos];
+      }
+      v[e] = rv;
+    }
+    sy();  // the stages have been read by every lane of the pair: the next group's lines may land
+    const int next = group + cpm;
+    if (next < ngroups) {
+      fetch(rst, r + pair_of(next) * 2 * N);
+      if (PRO) fetch(wst, w + pair_of(next) * 2 * N);
+    }
+    cp_async_commit();
+    if (PRO && active) {
+      GLIA_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const int pos = F::template loc<0>(t, e / F::R(0), e % F::R(0));
+        r[la + pos] = v[e].x;
+        r[lb + pos] = v[e].y;
+      }
+    }
+    F::forward(v, tw, sm, am, sy, t);
+    // scatter by frequency, then untangle the two real spectra
+    sy();
+    GLIA_UNROLL
+    for (int g = 0; g < F::Gp(F::P - 1); ++g) {
+      const int kb = F::kbase(t, g);
+      GLIA_UNROLL
+      for (int cc = 0; cc < F::RL; ++cc) {
+        const int k = kb + F::KSTEP * cc;
+        sm[k + (k >> 4)] = v[g * F::RL + cc];
+      }
+    }
+    sy();
+    const long oa = pair * 2 * (N / 2), ob = oa + N / 2;
+    GLIA_UNROLL
+    for (int j = 0; j < E / 2; ++j) {
+      const int k = t + TPL * j;
+      const int kn = (N - k) & (N - 1);
+      const cplx<T> zk = sm[k + (k >> 4)], zn = sm[kn + (kn >> 4)];
+      cplx<T> A = {(T)0.5 * (zk.x + zn.x), (T)0.5 * (zk.y - zn.y)};
+      cplx<T> B = {(T)0.5 * (zk.y + zn.y), (T)-0.5 * (zk.x - zn.x)};
+      if (k == 0) {
+        const cplx<T> zh = sm[N / 2 + ((N / 2) >> 4)];
+        A = {zk.x, zh.x};
+        B = {zk.y, zh.y};
+      }
+      if (active) { shat[oa + k] = A; shat[ob + k] = B; }
+    }
+    sy();  // the exchange region is rewritten by the next group's forward transform
+  }
+  cp_async_wait<0>();
 }
 
 }  // namespace glia
