@@ -756,7 +756,7 @@ class Engine : public EngineBase {
       if constexpr (r2cpipe_fits<T, N>()) {  // persistent warp-private pipelined form (sweeps_zpipe.cuh)
         const int ngroups = zgroups<N>(), cpm = cpm_zpipe2<N>();
         // (the r <- r - a w form at 512-point lines keeps the one-group-per-CTA kernel: it runs at the copy rate there,
-        // 328 us against 350 us pipelined, profiles/r3a_r2cpipe_ab.txt; an ensemble handle needs the member-aware form)
+        // 328 us against 350 us pipelined, profiles/r2za_r2cpipe_ab.txt; an ensemble handle needs the member-aware form)
         if (wv && (N < 512 || nb > 1))
           LP("kz_r2c.axpy", kz_r2c_pipe<T, N, 1>, dim3((unsigned)(cpm * nb)), dim3(zthreads<N>()), r2cpipe_smem<T, N>(), st,
              lines_z_member(), ngroups, rin, wv, (const double*)(scal + S_A), shat, (const C*)tw[2], done, cpm);

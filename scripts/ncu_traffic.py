@@ -8,14 +8,15 @@ import sys
 
 TAGS = [  # (regex on the ncu kernel name, bench tag)
     (r"ks_c2c_pipe<", "ks_c2c.y"),
-    (r"kz_c2r<\w+, \d+, 2>", "kz_c2r.rz"),
+    (r"kz_c2r(_pipe)?<\w+, \d+, 2>", "kz_c2r.rz"),
     (r"k_cg_update<", "k_cg_update"),
     (r"kz_deriv2_pipe<", "kz_deriv2"),
     (r"ks_deriv2_pipe<\w+, \d+, 1,", "ks_deriv2.y"),
     (r"ks_deriv2_pipe<\w+, \d+, 3,", "ks_deriv2.x.matvec"),
     (r"ks_deriv2_pipe<\w+, \d+, 4,", "ks_deriv2.x.rhs"),
-    (r"kz_r2c<\w+, \d+, 1>", "kz_r2c.axpy"),
-    (r"kz_r2c<\w+, \d+, 0>", "kz_r2c"),
+    (r"kz_r2c(_pipe)?<\w+, \d+, 1>", "kz_r2c.axpy"),
+    (r"kz_r2c(_pipe)?<\w+, \d+, 0>", "kz_r2c"),
+    (r"kz_c2r(_pipe)?<\w+, \d+, 1>", "kz_c2r.norm"),
     (r"ks_pc_pipe<", "ks_pc"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
