@@ -106,6 +106,17 @@ def test_z_sweep_three_pass_lines(B, dtype):
     assert e1 < budget and e2 < budget
 
 
+@pytest.mark.parametrize("n,dtype", [((32, 32, 128), np.float32), ((32, 32, 256), np.float32),
+                                     ((32, 32, 512), np.float32), ((32, 32, 128), np.float64)])
+def test_pcg_long_z_lines(B, n, dtype):
+    """128-, 256- and 512-point z lines through the whole PCG loop: the persistent warp-private r2c / c2r sweeps of the
+    preconditioner (two-pass and three-pass plans; double precision at 128 points takes the one-group-per-CTA forms)."""
+    r = Cs.case_forward_adjoint(B, n, dtype, nt=1, dt=0.05, with_grad=False)
+    assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], r
+    tol = Cs.TOL[np.dtype(dtype)]
+    assert r["cT"] < tol and r["p0"] < tol, r
+
+
 def test_first_order_splitting(B):
     r = Cs.case_forward_adjoint(B, 32, np.float64, nt=2, dt=0.05, order=1)
     assert r["its_state"][0] == r["its_state"][1] and r["its_adj"][0] == r["its_adj"][1], r
