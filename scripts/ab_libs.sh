@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of library builds on one B200:  gpurun --timeout 900 -- 'bash scripts/ab_libs.sh <tag> <name> [<name> ...]'
+# A/B of library builds on one B200 (how every profiles/r2[p-z]*_ab.txt of round 2 was taken; variants are built with
+# scripts/build_variant.sh or by copying libglia_rd.so aside before a rebuild):  gpurun --timeout 900 -- 'bash scripts/ab_libs.sh <tag> <name> [<name> ...]'
 # <name> -> glia_b200/lib/libglia_rd_<name>.so ("default" -> libglia_rd.so).  256^3 twice per library (interleaved),
 # 512^3 once; a parity subset runs first on the LAST library named.  Output: gpurun_out/<tag>_*.json, <tag>_ab.txt
 set -u
